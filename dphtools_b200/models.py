@@ -1,0 +1,121 @@
+"""Built-in model functions (float64 numpy) and their analytic Jacobians.
+
+The reference ships no Gaussian PSF model; these callables are the
+new API surface of this package.  Each one has the scipy ``f(xdata, *params)`` signature, so it can be
+handed to ``scipy.optimize.curve_fit`` or to the reference's ``dphtools.utils.lm.curve_fit`` unchanged,
+and carries ``model_id`` / ``n_param`` / ``jac`` attributes that :func:`dphtools_b200.curve_fit` uses as
+the dispatch key for the CUDA kernels.  ``multi_exp`` follows the reference's convention
+(``dphtools/utils/fitfuncs.py:20-52``): parameters ``(a0, k0, a1, k1, ..., [offset])``, the offset is
+present iff the number of parameters is odd.
+
+Conventions:
+
+* 2-D models take ``xdata = np.stack([xx.ravel(), yy.ravel()])`` with ``xx`` the column index and
+  ``yy`` the row index of a row-major ROI, integer pixel coordinates ``0..n-1``.
+* ``gauss2d``:  ``amp * exp(-((x-x0)^2 + (y-y0)^2) / (2 sigma^2)) + offset``
+* ``gauss2d_elliptical``: ``u =  c (x-x0) + s (y-y0)``, ``v = -s (x-x0) + c (y-y0)``,
+  ``amp * exp(-(u^2/sigma_x^2 + v^2/sigma_y^2)/2) + offset`` with ``c, s = cos, sin(theta)``.
+"""
+
+import numpy as np
+
+# numeric ids shared with include/dphlm.h (dphlm_model)
+MODEL_GAUSS2D = 0
+MODEL_GAUSS2D_ELLIPTICAL = 1
+MODEL_MULTI_EXP = 2
+
+
+def gauss2d(xy, amp, x0, y0, sigma, offset):
+    """Symmetric 2-D Gaussian, 5 parameters ``(amp, x0, y0, sigma, offset)``."""
+    dx = xy[0] - x0
+    dy = xy[1] - y0
+    return amp * np.exp(-(dx * dx + dy * dy) / (2.0 * sigma * sigma)) + offset
+
+
+def gauss2d_jac(xy, amp, x0, y0, sigma, offset):
+    """Jacobian of :func:`gauss2d`, shape ``(M, 5)`` (row = pixel, column = parameter)."""
+    dx = xy[0] - x0
+    dy = xy[1] - y0
+    r2 = dx * dx + dy * dy
+    s2 = sigma * sigma
+    e = np.exp(-r2 / (2.0 * s2))
+    ae = amp * e
+    return np.stack([e, ae * dx / s2, ae * dy / s2, ae * r2 / (s2 * sigma), np.ones_like(e)], axis=1)
+
+
+def gauss2d_elliptical(xy, amp, x0, y0, sigma_x, sigma_y, theta, offset):
+    """Rotated elliptical 2-D Gaussian, 7 parameters."""
+    c, s = np.cos(theta), np.sin(theta)
+    dx = xy[0] - x0
+    dy = xy[1] - y0
+    u = c * dx + s * dy
+    v = -s * dx + c * dy
+    return amp * np.exp(-0.5 * (u * u / sigma_x**2 + v * v / sigma_y**2)) + offset
+
+
+def gauss2d_elliptical_jac(xy, amp, x0, y0, sigma_x, sigma_y, theta, offset):
+    """Jacobian of :func:`gauss2d_elliptical`, shape ``(M, 7)``."""
+    c, s = np.cos(theta), np.sin(theta)
+    dx = xy[0] - x0
+    dy = xy[1] - y0
+    u = c * dx + s * dy
+    v = -s * dx + c * dy
+    ax = 1.0 / sigma_x**2
+    ay = 1.0 / sigma_y**2
+    e = np.exp(-0.5 * (u * u * ax + v * v * ay))
+    ae = amp * e
+    return np.stack(
+        [
+            e,
+            ae * (u * ax * c - v * ay * s),
+            ae * (u * ax * s + v * ay * c),
+            ae * u * u * ax / sigma_x,
+            ae * v * v * ay / sigma_y,
+            ae * u * v * (ay - ax),
+            np.ones_like(e),
+        ],
+        axis=1,
+    )
+
+
+def multi_exp(xdata, *args):
+    r"""Sum of exponentials ``offset + sum_i a_i exp(-k_i x)`` (reference ``fitfuncs.py:20-34``)."""
+    xdata = np.asarray(xdata, dtype=float)
+    n_exp = len(args) // 2
+    res = np.full_like(xdata, args[-1] if len(args) % 2 else 0.0)
+    for i in range(n_exp):
+        res = res + args[2 * i] * np.exp(-args[2 * i + 1] * xdata)
+    return res
+
+
+def multi_exp_jac(xdata, *args):
+    """Jacobian of :func:`multi_exp` (reference ``fitfuncs.py:37-52``), shape ``(M, len(args))``."""
+    xdata = np.asarray(xdata, dtype=float)
+    cols = []
+    for i in range(len(args) // 2):
+        e = np.exp(-args[2 * i + 1] * xdata)
+        cols += [e, -args[2 * i] * xdata * e]
+    if len(args) % 2:
+        cols.append(np.ones_like(xdata))
+    return np.stack(cols, axis=1)
+
+
+def _tag(func, jac, model_id, n_param, name):
+    func.jac = jac
+    func.model_id = model_id
+    func.n_param = n_param  # None: taken from len(p0)
+    func.model_name = name
+    return func
+
+
+_tag(gauss2d, gauss2d_jac, MODEL_GAUSS2D, 5, "gauss2d")
+_tag(gauss2d_elliptical, gauss2d_elliptical_jac, MODEL_GAUSS2D_ELLIPTICAL, 7, "gauss2d_elliptical")
+_tag(multi_exp, multi_exp_jac, MODEL_MULTI_EXP, None, "multi_exp")
+
+BUILTIN = {m.model_name: m for m in (gauss2d, gauss2d_elliptical, multi_exp)}
+
+
+def roi_grid(height, width):
+    """``xdata`` for a row-major ``height x width`` ROI: ``(2, M)`` array of (column, row) indices."""
+    yy, xx = np.mgrid[0:height, 0:width]
+    return np.stack([xx.ravel(), yy.ravel()]).astype(float)
