@@ -1,0 +1,847 @@
+// lm_core.cuh -- the batched Levenberg-Marquardt / Poisson-MLE fitter, one fit per lane-group.
+//
+// This header is the whole numerical algorithm.  It is written once and compiled twice:
+//   * by nvcc for sm_100a (lm_kernels.cu): a fit is owned by a group of G lanes of a warp, the
+//     per-pixel state lives in shared memory, partial sums are combined with warp shuffles;
+//   * by g++ with G = 1 (oracle/host_emu/host_emulation.cpp) so that the CPU test-suite can execute the very
+//     same fp32 logic against the float64 oracle without a GPU.  That host build is test
+//     infrastructure; the product path is the CUDA build only.
+//
+// What it replaces (reference file:line, upstream dphtools):
+//   stage A  scipy.optimize.curve_fit -> MINPACK lmder/lmpar pre-fit   dphtools/utils/lm.py:642-648
+//            (algorithm text: notebooks/lmder.f:186-452, notebooks/lmpar.f:100-264), restated over the
+//            normal equations A = J^T J, g = J^T r instead of a QR factorisation;
+//   stage B  lm()                                                      dphtools/utils/lm.py:221-507
+//            with _chi2_ls/_update_ls (lm.py:30-52), _chi2_mle/_update_mle (lm.py:55-103) and the
+//            non-negativity clamps (lm.py:106-132).
+//
+// fp32 and the 1.49e-8 tolerances.  The reference decides accept/reject and convergence from
+// differences of chi-square values that are ~1e-8 of chi-square itself -- below fp32 resolution
+// (SURVEY.md 7.3).  Here chi-square differences are never formed from two sums.  Every model provides
+// delta(): f(x+d) - f(x) per pixel computed from the STEP d (relative error ~1e-6, not absolute
+// error ~1e-7 f), and the reductions are accumulated per pixel as
+//      LS : -delta (r + delta/2)              MLE: -delta + y log1p(delta / f_old)
+// so that "actual" and "predicted" keep ~1e-6 relative accuracy down to 1e-10.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DPH_HD __host__ __device__ __forceinline__
+#else
+#define DPH_HD inline
+#endif
+
+namespace dphlm {
+
+// ------------------------------------------------------------------------------------------ math
+#if defined(__CUDA_ARCH__)
+DPH_HD float f_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DPH_HD float f_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DPH_HD float f_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DPH_HD float f_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DPH_HD float f_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+DPH_HD float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+DPH_HD bool f_finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
+#else
+DPH_HD float f_ex2(float x) { return exp2f(x); }
+DPH_HD float f_lg2(float x) { return log2f(x); }
+DPH_HD float f_rcp(float x) { return 1.0f / x; }
+DPH_HD float f_rsqrt(float x) { return 1.0f / sqrtf(x); }
+DPH_HD float f_sqrt(float x) { return sqrtf(x); }
+DPH_HD float f_fma(float a, float b, float c) { return fmaf(a, b, c); }
+DPH_HD bool f_finite(float x) { return std::isfinite(x); }
+#endif
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kInf = __builtin_huge_valf();
+
+// log1p(u), relative accuracy ~1e-7 for |u| <= 1/8 (Taylor, degree 8), lg2-based beyond.
+DPH_HD float log1p_acc(float u) {
+    float p = -0.125f;
+    p = f_fma(p, u, 1.0f / 7.0f);
+    p = f_fma(p, u, -1.0f / 6.0f);
+    p = f_fma(p, u, 0.2f);
+    p = f_fma(p, u, -0.25f);
+    p = f_fma(p, u, 1.0f / 3.0f);
+    p = f_fma(p, u, -0.5f);
+    p = f_fma(p * u, u, u);
+    float big = kLn2 * f_lg2(fmaxf(1.0f + u, 1e-37f));
+    return fabsf(u) <= 0.125f ? p : big;
+}
+
+// expm1(a) for |a| <= 1/8 (Taylor, degree 7); callers handle larger |a| by direct differences.
+DPH_HD float expm1_small(float a) {
+    float p = 1.0f / 5040.0f;
+    p = f_fma(p, a, 1.0f / 720.0f);
+    p = f_fma(p, a, 1.0f / 120.0f);
+    p = f_fma(p, a, 1.0f / 24.0f);
+    p = f_fma(p, a, 1.0f / 6.0f);
+    p = f_fma(p, a, 0.5f);
+    return f_fma(p * a, a, a);
+}
+constexpr float kSmallArg = 0.125f;
+
+// ------------------------------------------------------------------------------- small dense algebra
+// packed upper triangle, row-major: (i,j), i <= j
+template <int P>
+DPH_HD constexpr int tri(int i, int j) { return i * P - (i * (i - 1)) / 2 + (j - i); }
+template <int P>
+struct NT { static constexpr int value = P * (P + 1) / 2; };
+
+// Cholesky factor of (A + lam * diag(D)): U^T U, stored packed with the RECIPROCAL diagonal.
+// Returns false on a non-positive or non-finite pivot (the reference's LinAlgError branch, lm.py:426).
+template <int P>
+DPH_HD bool chol_factor(const float* A, const float* D, float lam, float* U) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        float d = f_fma(lam, D[i], A[tri<P>(i, i)]);
+#pragma unroll
+        for (int k = 0; k < i; ++k) d = f_fma(-U[tri<P>(k, i)], U[tri<P>(k, i)], d);
+        ok = ok && (d > 0.0f) && f_finite(d);
+        float rinv = f_rsqrt(d);
+        U[tri<P>(i, i)] = rinv;
+#pragma unroll
+        for (int j = i + 1; j < P; ++j) {
+            float s = A[tri<P>(i, j)];
+#pragma unroll
+            for (int k = 0; k < i; ++k) s = f_fma(-U[tri<P>(k, i)], U[tri<P>(k, j)], s);
+            U[tri<P>(i, j)] = s * rinv;
+        }
+    }
+    return ok;
+}
+
+// z = U^-T b (forward substitution), returns |z|^2
+template <int P>
+DPH_HD float chol_forward(const float* U, const float* b, float* z) {
+    float n2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        float s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s = f_fma(-U[tri<P>(k, i)], z[k], s);
+        z[i] = s * U[tri<P>(i, i)];
+        n2 = f_fma(z[i], z[i], n2);
+    }
+    return n2;
+}
+
+// x = -(U^T U)^-1 g
+template <int P>
+DPH_HD void chol_solve_neg(const float* U, const float* g, float* x) {
+    float z[P];
+    chol_forward<P>(U, g, z);
+#pragma unroll
+    for (int i = P - 1; i >= 0; --i) {
+        float s = z[i];
+#pragma unroll
+        for (int k = i + 1; k < P; ++k) s = f_fma(-U[tri<P>(i, k)], x[k], s);
+        x[i] = s * U[tri<P>(i, i)];
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) x[i] = -x[i];
+}
+
+template <int P>
+DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        float t = 0.5f * A[tri<P>(i, i)] * p[i];
+#pragma unroll
+        for (int j = i + 1; j < P; ++j) t = f_fma(A[tri<P>(i, j)], p[j], t);
+        s = f_fma(2.0f * p[i], t, s);
+    }
+    return s;
+}
+
+// --------------------------------------------------------------------------------------- models
+// A model describes one pixel: prepared parameters (Par), the stored exponentials (NE per pixel),
+// the model value, its Jacobian row, the accurate step difference delta() and J(x_old).d .
+// Pixel coordinates arrive as (cx, cy); 1-D models use cx only.
+
+struct Gauss2D {  // amp, x0, y0, sigma, offset
+    static constexpr int P = 5, NE = 1;
+    struct Par { float amp, x0, y0, sig, off, s2, s3, nh; };
+    struct Step { float d0, d1, d2, d3, d4, h1, ds, c2, c3; };
+    struct Geo { float dx, dy, r2; };
+    DPH_HD static void prepare(const float* p, Par& q) {
+        q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
+        float is = f_rcp(q.sig);
+        q.s2 = is * is;
+        q.s3 = q.s2 * is;
+        q.nh = -0.5f * kLog2e * q.s2;
+    }
+    DPH_HD static void geometry(const Par& q, float cx, float cy, Geo& g) {
+        g.dx = cx - q.x0; g.dy = cy - q.y0; g.r2 = f_fma(g.dx, g.dx, g.dy * g.dy);
+    }
+    DPH_HD static void expo(const Par& q, const Geo& g, float* e) { e[0] = f_ex2(q.nh * g.r2); }
+    DPH_HD static float value(const Par& q, const float* e) { return f_fma(q.amp, e[0], q.off); }
+    DPH_HD static void jac(const Par& q, const Geo& g, const float* e, float* J) {
+        float t = q.amp * e[0] * q.s2;
+        J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = q.amp * e[0] * q.s3 * g.r2; J[4] = 1.0f;
+    }
+    DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
+        s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3]; s.d4 = d[4];
+        s.h1 = 0.5f * b.s2;                                              // 1/(2 sigma_new^2)
+        s.ds = -d[3] * (2.0f * a.sig + d[3]) * 0.5f * a.s2 * b.s2;       // 1/(2 s_n^2) - 1/(2 s_o^2)
+        s.c2 = a.amp * a.s2; s.c3 = a.amp * a.s3 * d[3];
+    }
+    // ga/ea: geometry and exponentials at the OLD point, eb at the new one
+    DPH_HD static float delta(const Par& a, const Step& s, const Geo& ga, const float* ea, const float* eb) {
+        float dr2 = -s.d1 * (2.0f * ga.dx - s.d1) - s.d2 * (2.0f * ga.dy - s.d2);
+        float darg = -f_fma(dr2, s.h1, ga.r2 * s.ds);
+        float de = fabsf(darg) <= kSmallArg ? ea[0] * expm1_small(darg) : eb[0] - ea[0];
+        return f_fma(s.d0, eb[0], f_fma(a.amp, de, s.d4));
+    }
+    DPH_HD static float jdx(const Par& a, const Step& s, const Geo& ga, const float* ea) {
+        float lin = f_fma(s.c2, f_fma(ga.dx, s.d1, ga.dy * s.d2), s.c3 * ga.r2);
+        return f_fma(ea[0], s.d0 + lin, s.d4);
+    }
+};
+
+struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
+    static constexpr int P = 7, NE = 1;
+    struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy; };
+    struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day; };
+    struct Geo { float dx, dy, u, v; };
+    DPH_HD static void prepare(const float* p, Par& q) {
+        q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];
+#if defined(__CUDA_ARCH__)
+        sincosf(q.th, &q.s, &q.c);
+#else
+        q.s = sinf(q.th); q.c = cosf(q.th);
+#endif
+        q.isx = f_rcp(q.sx); q.isy = f_rcp(q.sy);
+        q.ax = q.isx * q.isx; q.ay = q.isy * q.isy;
+    }
+    DPH_HD static void geometry(const Par& q, float cx, float cy, Geo& g) {
+        g.dx = cx - q.x0; g.dy = cy - q.y0;
+        g.u = f_fma(q.c, g.dx, q.s * g.dy);
+        g.v = f_fma(q.c, g.dy, -q.s * g.dx);
+    }
+    DPH_HD static void expo(const Par& q, const Geo& g, float* e) {
+        e[0] = f_ex2(-0.5f * kLog2e * f_fma(g.u * g.u, q.ax, g.v * g.v * q.ay));
+    }
+    DPH_HD static float value(const Par& q, const float* e) { return f_fma(q.amp, e[0], q.off); }
+    DPH_HD static void jac(const Par& q, const Geo& g, const float* e, float* J) {
+        float ae = q.amp * e[0];
+        float uax = g.u * q.ax, vay = g.v * q.ay;
+        J[0] = e[0];
+        J[1] = ae * f_fma(uax, q.c, -vay * q.s);
+        J[2] = ae * f_fma(uax, q.s, vay * q.c);
+        J[3] = ae * g.u * uax * q.isx;
+        J[4] = ae * g.v * vay * q.isy;
+        J[5] = ae * g.u * g.v * (q.ay - q.ax);
+        J[6] = 1.0f;
+    }
+    DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
+        s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3]; s.d4 = d[4]; s.d5 = d[5]; s.d6 = d[6];
+        s.cb = b.c; s.sb = b.s;
+        // cos/sin increments through the half-angle identities (no cancellation)
+        float hs, hc;
+        float thm = a.th + 0.5f * d[5];
+#if defined(__CUDA_ARCH__)
+        sincosf(thm, &hs, &hc);
+#else
+        hs = sinf(thm); hc = cosf(thm);
+#endif
+        float sh = sinf(0.5f * d[5]);
+        s.dc = -2.0f * hs * sh;
+        s.dsn = 2.0f * hc * sh;
+        s.axb = b.ax; s.ayb = b.ay;
+        s.dax = -d[3] * (2.0f * a.sx + d[3]) * a.ax * b.ax;
+        s.day = -d[4] * (2.0f * a.sy + d[4]) * a.ay * b.ay;
+    }
+    DPH_HD static float delta(const Par& a, const Step& s, const Geo& ga, const float* ea, const float* eb) {
+        float du = f_fma(s.dc, ga.dx, s.dsn * ga.dy) - f_fma(s.cb, s.d1, s.sb * s.d2);
+        float dv = f_fma(s.dc, ga.dy, -s.dsn * ga.dx) - f_fma(s.cb, s.d2, -s.sb * s.d1);
+        float du2 = du * f_fma(2.0f, ga.u, du);
+        float dv2 = dv * f_fma(2.0f, ga.v, dv);
+        float t = f_fma(du2, s.axb, ga.u * ga.u * s.dax) + f_fma(dv2, s.ayb, ga.v * ga.v * s.day);
+        float darg = -0.5f * t;
+        float de = fabsf(darg) <= kSmallArg ? ea[0] * expm1_small(darg) : eb[0] - ea[0];
+        return f_fma(s.d0, eb[0], f_fma(a.amp, de, s.d6));
+    }
+    DPH_HD static float jdx(const Par& a, const Step& s, const Geo& ga, const float* ea) {
+        float J[P];
+        jac(a, ga, ea, J);
+        float r = s.d6;
+        r = f_fma(J[0], s.d0, r); r = f_fma(J[1], s.d1, r); r = f_fma(J[2], s.d2, r);
+        r = f_fma(J[3], s.d3, r); r = f_fma(J[4], s.d4, r); r = f_fma(J[5], s.d5, r);
+        return r;
+    }
+};
+
+// sum of NEXP exponentials (+ offset): a0, k0, a1, k1, ..., [offset]   (fitfuncs.py:20-52)
+template <int NEXP, bool OFFSET>
+struct MultiExp {
+    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = NEXP;
+    struct Par { float a[NEXP], k[NEXP], off; };
+    struct Step { float da[NEXP], dk[NEXP], doff; };
+    struct Geo { float x; };
+    DPH_HD static void prepare(const float* p, Par& q) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) { q.a[i] = p[2 * i]; q.k[i] = p[2 * i + 1]; }
+        q.off = OFFSET ? p[2 * NEXP] : 0.0f;
+    }
+    DPH_HD static void geometry(const Par&, float cx, float, Geo& g) { g.x = cx; }
+    DPH_HD static void expo(const Par& q, const Geo& g, float* e) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) e[i] = f_ex2(-kLog2e * q.k[i] * g.x);
+    }
+    DPH_HD static float value(const Par& q, const float* e) {
+        float f = q.off;
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) f = f_fma(q.a[i], e[i], f);
+        return f;
+    }
+    DPH_HD static void jac(const Par& q, const Geo& g, const float* e, float* J) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[i]; J[2 * i + 1] = -q.a[i] * g.x * e[i]; }
+        if (OFFSET) J[2 * NEXP] = 1.0f;
+    }
+    DPH_HD static void prepare_step(const Par&, const Par&, const float* d, Step& s) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) { s.da[i] = d[2 * i]; s.dk[i] = d[2 * i + 1]; }
+        s.doff = OFFSET ? d[2 * NEXP] : 0.0f;
+    }
+    DPH_HD static float delta(const Par& a, const Step& s, const Geo& ga, const float* ea, const float* eb) {
+        float r = s.doff;
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) {
+            float darg = -s.dk[i] * ga.x;
+            float de = fabsf(darg) <= kSmallArg ? ea[i] * expm1_small(darg) : eb[i] - ea[i];
+            r = f_fma(s.da[i], eb[i], f_fma(a.a[i], de, r));
+        }
+        return r;
+    }
+    DPH_HD static float jdx(const Par& a, const Step& s, const Geo& ga, const float* ea) {
+        float r = s.doff;
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) r = f_fma(ea[i], f_fma(-a.a[i] * ga.x, s.dk[i], s.da[i]), r);
+        return r;
+    }
+};
+
+// ------------------------------------------------------------------------------ lane group / storage
+// Per-fit pixel state, pointer based so that the device (shared memory) and host builds share code.
+//   y[M]          data (MLE: already clamped to >= 0)
+//   e[2][NE][M]   stored exponentials, double buffered: `cur` is the accepted point, 1-cur the trial
+//   cxy[M]        pixel coordinates (x, y), shared by all fits
+struct Coord { float x, y; };
+
+template <int NE>
+struct PixelState {
+    float* y;
+    float* e;  // [2][NE][M]
+    const Coord* cxy;
+    int M;
+    int cur;
+    DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * M; }
+};
+
+// Group of G lanes.  On the host G == 1 and the reductions are the identity.
+template <int G>
+struct Lanes {
+    int lane;  // index inside the group
+#if defined(__CUDA_ARCH__)
+    DPH_HD float sum(float v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    DPH_HD int any(int v) const {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    DPH_HD static bool warp_any(bool v) { return __any_sync(0xffffffffu, v); }
+#else
+    DPH_HD float sum(float v) const { return v; }
+    DPH_HD int any(int v) const { return v; }
+    DPH_HD static bool warp_any(bool v) { return v; }
+#endif
+    template <int N>
+    DPH_HD void sum_all(float* v) const {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = sum(v[i]);
+    }
+};
+
+// ------------------------------------------------------------------------------------ pixel passes
+template <int P>
+struct Normal {  // per-lane partial sums of one pass
+    float A[NT<P>::value];
+    float g[P];
+    float actual, predicted;  // chi2(old) - chi2(trial), chi2(old) - chi2(trial + J_old d)
+    int flags;                // bit0: non-finite model value, bit1: predicted model < 0 somewhere
+    DPH_HD void clear() {
+#pragma unroll
+        for (int i = 0; i < NT<P>::value; ++i) A[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) g[i] = 0.0f;
+        actual = predicted = 0.0f;
+        flags = 0;
+    }
+};
+
+template <int P>
+DPH_HD void accumulate(Normal<P>& n, const float* J, float w, float res) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        float wj = w * J[i];
+#pragma unroll
+        for (int j = i; j < P; ++j) n.A[tri<P>(i, j)] = f_fma(wj, J[j], n.A[tri<P>(i, j)]);
+        n.g[i] = f_fma(J[i], res, n.g[i]);
+    }
+}
+
+// Poisson term  t(f) = f - y ln(f / y)  with the reference's zeroing rule (lm.py:70-78); slow path.
+DPH_HD float mle_term_direct(float f, float y) {
+    float l = (y > 0.0f && f > 0.0f) ? y * kLn2 * (f_lg2(f) - f_lg2(y)) : 0.0f;
+    return f - l;
+}
+DPH_HD float clamp_nonneg(float f) { return f <= 0.0f ? 0.0f : f; }  // lm.py:117
+
+// MLE weights at a model value f (already clamped): w = y/f^2, res = 1 - y/f; invalid -> (0, 1)  (lm.py:86-102)
+DPH_HD void mle_weights(float f, float y, float& w, float& res) {
+    float rf = f_rcp(f);
+    float yf = y * rf;
+    float ww = yf * rf;
+    bool ok = (f > 0.0f) && f_finite(ww);
+    w = ok ? ww : 0.0f;
+    res = ok ? 1.0f - yf : 1.0f;
+}
+
+// First evaluation at a point: stores the exponentials in buffer `cur`, accumulates A, g and the
+// chi-square itself (directly; only needed to ~1e-6 relative for the ftol right-hand sides).
+template <class Mo, bool MLE, int G>
+DPH_HD void init_pass(const Lanes<G>& ln, PixelState<Mo::NE>& px, const typename Mo::Par& q, Normal<Mo::P>& n, float& chisq) {
+    constexpr int P = Mo::P;
+    n.clear();
+    float chi = 0.0f;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+    for (int i = ln.lane; i < px.M; i += G) {
+        typename Mo::Geo geo;
+        float e[Mo::NE], J[P];
+        Mo::geometry(q, px.cxy[i].x, px.cxy[i].y, geo);
+        Mo::expo(q, geo, e);
+#pragma unroll
+        for (int j = 0; j < Mo::NE; ++j) px.ebuf(px.cur, j)[i] = e[j];
+        float f = Mo::value(q, e);
+        float y = px.y[i];
+        if (!f_finite(f)) n.flags |= 1;
+        Mo::jac(q, geo, e, J);
+        if (MLE) {
+            f = clamp_nonneg(f);
+            float w, res;
+            mle_weights(f, y, w, res);
+            accumulate<P>(n, J, w, res);
+            chi += mle_term_direct(f, y) - y;
+        } else {
+            float r = f - y;
+            accumulate<P>(n, J, 1.0f, r);
+            chi = f_fma(0.5f * r, r, chi);
+        }
+    }
+    ln.template sum_all<NT<P>::value>(n.A);
+    ln.template sum_all<P>(n.g);
+    chisq = ln.sum(chi);
+    n.flags = ln.any(n.flags);
+}
+
+// Trial evaluation at q1 = q0 + d.  Reads the exponentials of the accepted point (buffer cur), writes
+// the trial ones (buffer 1-cur), accumulates the chi-square reductions from per-pixel differences and,
+// speculatively, A and g at the trial point.  QUIRK (lm.py:446-449): the predicted model is
+// f(x_new) + J(x_old) d.
+template <class Mo, bool MLE, bool PRED, int G>
+DPH_HD void trial_pass(const Lanes<G>& ln, PixelState<Mo::NE>& px, const typename Mo::Par& q0, const typename Mo::Par& q1,
+                       const typename Mo::Step& st, Normal<Mo::P>& n) {
+    constexpr int P = Mo::P;
+    n.clear();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+    for (int i = ln.lane; i < px.M; i += G) {
+        typename Mo::Geo g0, g1;
+        float e0[Mo::NE], e1[Mo::NE], J[P];
+        float cx = px.cxy[i].x, cy = px.cxy[i].y;
+        Mo::geometry(q0, cx, cy, g0);
+        Mo::geometry(q1, cx, cy, g1);
+#pragma unroll
+        for (int j = 0; j < Mo::NE; ++j) e0[j] = px.ebuf(px.cur, j)[i];
+        Mo::expo(q1, g1, e1);
+#pragma unroll
+        for (int j = 0; j < Mo::NE; ++j) px.ebuf(1 - px.cur, j)[i] = e1[j];
+        float y = px.y[i];
+        float f0 = Mo::value(q0, e0);
+        float f1 = Mo::value(q1, e1);
+        if (!f_finite(f1)) n.flags |= 1;
+        float dl = Mo::delta(q0, st, g0, e0, e1);
+        Mo::jac(q1, g1, e1, J);
+        if (MLE) {
+            float f0c = clamp_nonneg(f0), f1c = clamp_nonneg(f1);
+            float rf0 = f_rcp(f0c);
+            bool reg = (f0c > 0.0f) && (f1c > 0.0f);
+            if (reg) {
+                n.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
+            } else {
+                n.actual += mle_term_direct(f0c, y) - mle_term_direct(f1c, y);
+            }
+            if (PRED) {
+                float jd = Mo::jdx(q0, st, g0, e0);
+                float fp = f1c + jd;
+                if (fp < 0.0f) n.flags |= 2;
+                if (reg && fp > 0.0f) {
+                    float dp = dl + jd;
+                    n.predicted += f_fma(y, log1p_acc(dp * rf0), -dp);
+                } else {
+                    n.predicted += mle_term_direct(f0c, y) - mle_term_direct(fp, y);
+                }
+            }
+            float w, res;
+            mle_weights(f1c, y, w, res);
+            accumulate<P>(n, J, w, res);
+        } else {
+            float r0 = f0 - y;
+            n.actual = f_fma(-dl, f_fma(0.5f, dl, r0), n.actual);
+            if (PRED) {
+                float dp = dl + Mo::jdx(q0, st, g0, e0);
+                n.predicted = f_fma(-dp, f_fma(0.5f, dp, r0), n.predicted);
+            }
+            accumulate<P>(n, J, 1.0f, f1 - y);
+        }
+    }
+    ln.template sum_all<NT<P>::value>(n.A);
+    ln.template sum_all<P>(n.g);
+    n.actual = ln.sum(n.actual);
+    if (PRED) n.predicted = ln.sum(n.predicted);
+    n.flags = ln.any(n.flags);
+}
+
+// ------------------------------------------------------------------------------------- options/result
+struct Options {
+    float ftol, xtol, gtol, factor;
+    int maxfev;  // <= 0: 100 * (P + 1)
+};
+
+template <int P>
+struct FitResult {
+    float x[P];
+    float p_ls[P];
+    float chisq;
+    int info;      // stage B exit (lm.py): 1, 2, 4, 5; -ier when the stage-A pre-fit ends with ier not in 1..4
+    int nfev;      // stage B: zero-based index of the last trip (lm.py:489)
+    int nfev_ls;   // stage A: function evaluations (MINPACK nfev)
+    int n_acc, n_rej;
+};
+
+// ------------------------------------------------------------------------- stage A: MINPACK lmder
+// lmpar (notebooks/lmpar.f:100-264) over the normal equations: find par >= 0 such that the step
+// p = -(A + par D)^-1 g has |sqrt(D) p| within 10% of delta.  D holds the SQUARED scale factors.
+template <int P>
+DPH_HD void lmpar_normal(const float* A, const float* g, const float* D, float delta, float& par, float* p, float& pnorm) {
+    constexpr float dwarf = 1.17549435e-38f;
+    float U[NT<P>::value], w[P], z[P];
+    bool full_rank = chol_factor<P>(A, D, 0.0f, U);
+    float dxnorm, fp;
+    if (full_rank) {
+        chol_solve_neg<P>(U, g, p);
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) s = f_fma(D[i] * p[i], p[i], s);
+        dxnorm = sqrtf(s);
+        fp = dxnorm - delta;
+        if (fp <= 0.1f * delta) { par = 0.0f; pnorm = dxnorm; return; }
+    } else {
+        dxnorm = kInf; fp = kInf;
+    }
+    float parl = 0.0f;
+    if (full_rank) {
+        float rdx = 1.0f / dxnorm;
+#pragma unroll
+        for (int i = 0; i < P; ++i) w[i] = D[i] * p[i] * rdx;
+        float t2 = chol_forward<P>(U, w, z);
+        parl = (fp / delta) / t2;
+    }
+    float gn = 0.0f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) gn = f_fma(g[i] * g[i], 1.0f / D[i], gn);
+    float gnorm = sqrtf(gn);
+    float paru = gnorm / delta;
+    if (paru == 0.0f) paru = dwarf / fminf(delta, 0.1f);
+    par = fmaxf(par, parl);
+    par = fminf(par, paru);
+    if (par == 0.0f) par = full_rank ? gnorm / dxnorm : 0.0f;
+    for (int it = 1;; ++it) {
+        if (par == 0.0f) par = fmaxf(dwarf, 0.001f * paru);
+        bool ok = chol_factor<P>(A, D, par, U);
+        chol_solve_neg<P>(U, g, p);
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) s = f_fma(D[i] * p[i], p[i], s);
+        dxnorm = sqrtf(s);
+        float temp = fp;
+        fp = dxnorm - delta;
+        if (!ok || !f_finite(fp)) {  // not factorizable in fp32: push par up and retry (bounded by it == 10)
+            if (it == 10) break;
+            parl = fmaxf(parl, par);
+            par = fmaxf(2.0f * par, 0.001f * paru);
+            fp = temp;
+            continue;
+        }
+        if (fabsf(fp) <= 0.1f * delta || (parl == 0.0f && fp <= temp && temp < 0.0f) || it == 10) break;
+        float rdx = 1.0f / dxnorm;
+#pragma unroll
+        for (int i = 0; i < P; ++i) w[i] = D[i] * p[i] * rdx;
+        float t2 = chol_forward<P>(U, w, z);
+        float parc = (fp / delta) / t2;
+        if (fp > 0.0f) parl = fmaxf(parl, par);
+        if (fp < 0.0f) paru = fminf(paru, par);
+        par = fmaxf(parl, par + parc);
+    }
+    pnorm = dxnorm;
+}
+
+// ------------------------------------------------------------------------------------- one fit
+// Runs both stages for the fit owned by this lane group.  `active` is false for padding groups of a
+// partially filled warp: they execute the same instruction stream (the shuffles are warp-wide) but
+// their state is never written back.
+template <class Mo, bool MLE, int G>
+DPH_HD void fit_one(const Lanes<G>& ln, PixelState<Mo::NE>& px, const float* p0, const Options& opt, bool active,
+                    FitResult<Mo::P>& out) {
+    constexpr int P = Mo::P;
+    constexpr int NTP = NT<P>::value;
+    const int maxfev = opt.maxfev > 0 ? opt.maxfev : 100 * (P + 1);
+
+    float x[P], A[NTP], g[P], D[P], p[P];
+    typename Mo::Par q0, q1;
+    typename Mo::Step st;
+    Normal<P> nrm;
+#pragma unroll
+    for (int i = 0; i < P; ++i) x[i] = p0[i];
+
+    // ================================ stage A: least-squares pre-fit (MINPACK lmder, lm.py:642-648)
+    px.cur = 0;
+    Mo::prepare(x, q0);
+    float chi;  // 0.5 * fnorm^2
+    init_pass<Mo, false, G>(ln, px, q0, nrm, chi);
+#pragma unroll
+    for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
+#pragma unroll
+    for (int i = 0; i < P; ++i) g[i] = nrm.g[i];
+    int ier = 0;
+    if (nrm.flags & 1) ier = 9;  // non-finite start (scipy raises ValueError)
+    int nfev_ls = 1;
+    float par = 0.0f, delta = 0.0f, xnorm = 0.0f;
+    bool first = true;
+    bool running = active && ier == 0;
+    bool fresh = true;  // A, g belong to a newly accepted point: rescale (lmder.f:319-321)
+    while (Lanes<G>::warp_any(running)) {
+        float pnorm = 0.0f;
+        if (running) {
+            if (fresh) {
+                if (first) {
+#pragma unroll
+                    for (int i = 0; i < P; ++i) D[i] = A[tri<P>(i, i)] == 0.0f ? 1.0f : A[tri<P>(i, i)];
+                    float s = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) s = f_fma(D[i] * x[i], x[i], s);
+                    xnorm = sqrtf(s);
+                    delta = opt.factor * xnorm;
+                    if (delta == 0.0f) delta = opt.factor;
+                }
+                if (opt.gtol > 0.0f && chi > 0.0f) {  // lmder.f gnorm test
+                    float gnorm = 0.0f, rf = 1.0f / sqrtf(2.0f * chi);
+#pragma unroll
+                    for (int i = 0; i < P; ++i)
+                        if (A[tri<P>(i, i)] != 0.0f) gnorm = fmaxf(gnorm, fabsf(g[i] * rf / sqrtf(A[tri<P>(i, i)])));
+                    if (gnorm <= opt.gtol) ier = 4;
+                }
+#pragma unroll
+                for (int i = 0; i < P; ++i) D[i] = fmaxf(D[i], A[tri<P>(i, i)]);
+                fresh = false;
+            }
+            if (ier == 0) {
+                lmpar_normal<P>(A, g, D, delta, par, p, pnorm);
+                if (first) delta = fminf(delta, pnorm);
+            } else {
+                running = false;
+            }
+        }
+        if (!running) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) p[i] = 0.0f;
+        }
+        float xn[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) xn[i] = x[i] + p[i];
+        Mo::prepare(xn, q1);
+        Mo::prepare_step(q0, q1, p, st);
+        trial_pass<Mo, false, false, G>(ln, px, q0, q1, st, nrm);
+        if (running) {
+            ++nfev_ls;
+            float fn2 = 2.0f * chi;                 // fnorm^2
+            float actual = nrm.actual;
+            bool bad = (nrm.flags & 1) || !f_finite(actual);
+            // actred = 1 - (fnorm1/fnorm)^2 unless 0.1 fnorm1 >= fnorm  (lmder.f: actred = -1)
+            float actred = (!bad && (fn2 - 2.0f * actual) < 100.0f * fn2) ? 2.0f * actual / fn2 : -1.0f;
+            float t1 = quad_form<P>(A, p) / fn2;
+            float t2 = par * pnorm * pnorm / fn2;
+            float prered = t1 + 2.0f * t2;
+            float dirder = -(t1 + t2);
+            float ratio = prered != 0.0f ? actred / prered : 0.0f;
+            if (ratio <= 0.25f) {
+                float temp = actred >= 0.0f ? 0.5f : 0.5f * dirder / (dirder + 0.5f * actred);
+                if (bad || (fn2 - 2.0f * actual) >= 100.0f * fn2 || temp < 0.1f) temp = 0.1f;
+                delta = temp * fminf(delta, pnorm * 10.0f);
+                par = par / temp;
+            } else if (par == 0.0f || ratio >= 0.75f) {
+                delta = 2.0f * pnorm;
+                par = 0.5f * par;
+            }
+            if (ratio >= 1e-4f) {  // successful iteration
+#pragma unroll
+                for (int i = 0; i < P; ++i) x[i] = xn[i];
+                q0 = q1;
+                px.cur = 1 - px.cur;
+#pragma unroll
+                for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
+#pragma unroll
+                for (int i = 0; i < P; ++i) g[i] = nrm.g[i];
+                float s = 0.0f;
+#pragma unroll
+                for (int i = 0; i < P; ++i) s = f_fma(D[i] * x[i], x[i], s);
+                xnorm = sqrtf(s);
+                chi -= actual;
+                fresh = true;
+                first = false;
+            }
+            bool fconv = fabsf(actred) <= opt.ftol && prered <= opt.ftol && 0.5f * ratio <= 1.0f;
+            if (fconv) ier = 1;
+            if (delta <= opt.xtol * xnorm) ier = fconv ? 3 : 2;
+            if (ier == 0 && nfev_ls >= maxfev) ier = 5;
+            if (ier == 0 && !(delta > 0.0f)) ier = 7;
+            if (ier != 0) running = false;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) out.p_ls[i] = x[i];
+    out.nfev_ls = nfev_ls;
+
+    // ================================ stage B: the reference's lm() loop (lm.py:389-481)
+    bool okA = active && ier >= 1 && ier <= 4;
+    float dtd[P];
+    float chisq_old, lam;
+    Mo::prepare(x, q0);
+    init_pass<Mo, MLE, G>(ln, px, q0, nrm, chisq_old);
+#pragma unroll
+    for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
+#pragma unroll
+    for (int i = 0; i < P; ++i) { g[i] = nrm.g[i]; dtd[i] = A[tri<P>(i, i)]; }
+    {
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) s = f_fma(dtd[i] * x[i], x[i], s);
+        lam = sqrtf(s);                                            // lm.py:398
+        if (!(lam > 0.0f) || !f_finite(lam)) lam = 100.0f;         // lm.py:399-400
+    }
+    float xret[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) xret[i] = x[i];
+    float chisq_ret = chisq_old;
+    int info = 5, ev = 0, n_acc = 0, n_rej = 0;
+    running = okA;
+    if (maxfev <= 0) running = false;
+    float U[NTP];
+    while (Lanes<G>::warp_any(running)) {
+        bool live = false;
+        if (running) {
+            if (opt.gtol > 0.0f) {  // lm.py:358-363, 409-411
+                float gm = 0.0f;
+#pragma unroll
+                for (int i = 0; i < P; ++i) gm = fmaxf(gm, fabsf(g[i]));
+                if (gm <= opt.gtol) { info = 4; running = false; }
+            }
+        }
+        if (running) {
+            bool ok = chol_factor<P>(A, dtd, lam, U);
+            if (ok) {
+                chol_solve_neg<P>(U, g, p);
+#pragma unroll
+                for (int i = 0; i < P; ++i) ok = ok && f_finite(p[i]);
+            }
+            if (!ok) {
+                lam *= opt.factor;  // lm.py:426-428: the trip is consumed
+            } else {
+                float dn = 0.0f, xn2 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < P; ++i) { dn = f_fma(p[i], p[i], dn); xn2 = f_fma(x[i], x[i], xn2); }
+                if (sqrtf(dn) <= opt.xtol * (sqrtf(xn2) + opt.xtol)) {  // lm.py:365-367, 430-432
+                    info = 2; running = false;
+                } else {
+                    live = true;
+                }
+            }
+        }
+        if (!live) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) p[i] = 0.0f;
+        }
+        float xn[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) xn[i] = x[i] + p[i];
+        Mo::prepare(xn, q1);
+        Mo::prepare_step(q0, q1, p, st);
+        trial_pass<Mo, MLE, true, G>(ln, px, q0, q1, st, nrm);
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) xret[i] = xn[i];
+            float actual = nrm.actual;
+            float predicted = (nrm.flags & 2) ? -kInf : nrm.predicted;  // chi2 = +inf when the predicted model dips below 0 (lm.py:62-64)
+            chisq_ret = chisq_old - actual;
+            float rho = actual / predicted;
+            if (actual < 0.0f || predicted < 0.0f || !f_finite(rho)) rho = 0.0f;  // lm.py:454-463
+            if (rho > 1e-2f) {
+                if (actual <= opt.ftol * chisq_old) {  // lm.py:468-470
+                    info = 1; running = false;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < P; ++i) x[i] = xn[i];
+                    q0 = q1;
+                    px.cur = 1 - px.cur;
+                    chisq_old -= actual;
+#pragma unroll
+                    for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
+#pragma unroll
+                    for (int i = 0; i < P; ++i) { g[i] = nrm.g[i]; dtd[i] = fmaxf(dtd[i], A[tri<P>(i, i)]); }  // lm.py:474
+                    lam = fmaxf(lam * 0.2f, 1e-7f);  // lm.py:475
+                    ++n_acc;
+                }
+            } else {
+                lam = fminf(lam * 1.5f, 1e7f);  // lm.py:477
+                ++n_rej;
+            }
+        }
+        if (running) {
+            ++ev;
+            if (ev >= maxfev) { running = false; ev = maxfev - 1; }  // info stays 5 (lm.py:479-481)
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) out.x[i] = xret[i];
+    out.chisq = chisq_ret;
+    out.info = okA ? info : (ier == 0 ? -100 : -ier);
+    out.nfev = ev;
+    out.n_acc = n_acc;
+    out.n_rej = n_rej;
+}
+
+}  // namespace dphlm

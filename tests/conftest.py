@@ -8,21 +8,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
+from oracle.golden import load_golden  # noqa: E402
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-
-
-def load_golden(name):
-    """Golden set written by oracle/make_golden.py from the live reference."""
-    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-    g = {k: z[k] for k in z.files}
-    g["data"] = g["data"].astype(np.float32)
-    g["xaxis"] = g["xaxis"] if g["xaxis"].size else None
-    g["workload"], _, _, g["method"], g["model"] = [str(s) for s in g["meta"]]
-    return g
 
 
 @pytest.fixture(scope="session")
