@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Headline benchmark: Gaussian-PSF MLE fits/s on 11x11 ROIs (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
+    python bench.py --impl reference [...]                       # the reference algorithm on the host cores
+
+One "step" = one pass of the hot path over one batch of 1e5 synthetic Poisson-noised spots per GPU (weak
+scaling: each rank fits its own shard, no data-path collective).  `value` is whole-job
+fits/s with the inputs resident in HBM; `e2e` is the same through the public API with pinned HOST buffers
+(H2D + kernel + D2H inside the timed region).  The reference arm times the float64 oracle port of
+dphtools.utils.lm.curve_fit (scipy MINPACK pre-fit + lm(); the Python reference itself cannot travel to the
+GPU box) with one process per host core on a bounded sample of the same workload.
+"""
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOAD = "c2_gauss2d_11"
+ROI = 11
+N_FITS = 100_000          # per GPU and step
+N_SETS = 4                # distinct input sets rotated between steps: 4 x 48.4 MB > 126 MB L2
+METRIC = "Gaussian-PSF MLE fits/sec (11x11 ROI)"
+# algorithmic flops per pixel: setup, accepted / rejected MLE trip, LS pre-fit evaluation
+F_0, F_ACC, F_REJ, F_LS = 75, 93, 36, 73
+BYTES_PER_FIT = 4 * ROI * ROI + 4 * 5 + 4 * 5 + 12  # 536 B
+
+
+def _cpu_fit_chunk(args):
+    data, p0 = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from dphtools_b200 import models
+    from oracle import lm_oracle
+
+    out = lm_oracle.fit_batch(models.gauss2d, data, p0, "mle", models.roi_grid(ROI, ROI))
+    return out["popt"], out["info"], out["nfev"]
+
+
+def cpu_reference(data, p0, cores):
+    """Oracle port of the reference path on `cores` processes; returns (fits/s, popt, info, nfev)."""
+    import multiprocessing as mp
+
+    chunks = [(data[i::cores], p0[i::cores]) for i in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_fit_chunk, [(c[0][:2], c[1][:2]) for c in chunks])  # warm the workers (imports)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_fit_chunk, chunks)
+        dt = time.perf_counter() - t0
+    n = data.shape[0]
+    popt = np.empty((n, 5))
+    info = np.empty(n, np.int32)
+    nfev = np.empty(n, np.int32)
+    for i, r in enumerate(res):
+        popt[i::cores], info[i::cores], nfev[i::cores] = r
+    return n / dt, popt, info, nfev
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled through NVML while the benchmark runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self.stop_flag:
+                util = nv.nvmlDeviceGetUtilizationRates(h).gpu
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                if util > 0:
+                    self.samples.append(mhz)
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.reasons |= {v for k, v in names.items() if r & k}
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that, never fail the run
+            self.reasons.add("nvml_unavailable:" + type(e).__name__)
+
+    def summary(self):
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dphtools_b200 import synth
+
+    cores = os.cpu_count()
+    per_step = max(256, 400 * cores)  # ~400 fits per core and step: ~1.5-2 s per step
+    w = synth.WORKLOADS[WORKLOAD](per_step * (args.steps + args.warmup), seed=100)
+    rates = []
+    for s in range(args.steps + args.warmup):
+        sl = slice(s * per_step, (s + 1) * per_step)
+        rate, _, info, _ = cpu_reference(w["data"][sl], w["p0"][sl], cores)
+        if s >= args.warmup:
+            rates.append(rate)
+    value = float(np.mean(rates))
+    sample = "%d fits per step (11x11 sym-Gaussian MLE, same generator as the GPU arm), %d steps" % (per_step, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "1e5 symmetric 2D Gaussian MLE fits, 11x11 ROIs, photons 100-5000 (configs[1]); bounded sample per step", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--fits", type=int, default=N_FITS, help="fits per GPU and step")
+    ap.add_argument("--group-lanes", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import dphtools_b200 as dph
+    from dphtools_b200 import _lib, models, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n = args.fits
+
+    # ---- synthetic inputs: N_SETS distinct batches per rank (seeded), resident in HBM
+    sets = [synth.WORKLOADS[WORKLOAD](n, seed=1000 * rank + s) for s in range(N_SETS)]
+    d_data = [torch.from_numpy(s["data"]).to(dev) for s in sets]
+    d_p0 = [torch.from_numpy(s["p0"]).to(dev) for s in sets]
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    def step(i, counts=False):
+        return dph.curve_fit_batch(models.gauss2d, d_data[i % N_SETS], d_p0[i % N_SETS], "mle", return_counts=counts,
+                                   group_lanes=args.group_lanes)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        res = step(i)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # ---- the dominant (only) kernel alone: per-launch duration and algorithmic flops from its own counters
+    kt = []
+    flops = []
+    for i in range(min(args.steps, 8)):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = step(i, counts=True)
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b) * 1e-3)
+        c = r.counts.sum(0).double().cpu().numpy()
+        flops.append(ROI * ROI * (F_0 * n + F_ACC * c[1] + F_REJ * c[2] + F_LS * c[0]))
+    k_s = float(np.mean(kt))
+    achieved_tf = float(np.mean(flops)) / k_s / 1e12
+    props = torch.cuda.get_device_properties(dev)
+
+    # ---- end to end through the public API with pinned host buffers (H2D + fit + D2H per step)
+    lib = _lib.lib()
+    import ctypes
+
+    def pinned(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = lib.dphlm_host_alloc(nbytes)
+        assert ptr, "pinned allocation failed"
+        buf = (ctypes.c_char * nbytes).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
+
+    h_sets = []
+    for s in sets[:2]:
+        hd, p1 = pinned(s["data"].shape, np.float32)
+        hp, p2 = pinned(s["p0"].shape, np.float32)
+        hd[...] = s["data"]
+        hp[...] = s["p0"]
+        h_sets.append((hd, hp, p1, p2))
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r_host = dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t_e2e.item())
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        info = res.info.cpu().numpy()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = (sampler.max_mhz or peaks.get("sm_max_mhz") or 1965.0) * 1e6
+        fp32_peak_tf = props.multi_processor_count * 128 * 2 * sm_max / 1e12
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        out = {
+            "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": "1e5 symmetric 2D Gaussian MLE fits per GPU and step, 11x11 ROIs, photons 100-5000 (BASELINE configs[1])",
+                "fits_per_gpu_per_step": n, "sharding": "independent fits, contiguous shards, no collective",
+                "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2" % (N_SETS, N_SETS * n * ROI * ROI * 4 / 1e6),
+                "converged_fraction": float(((info >= 1) & (info <= 4)).mean()),
+            },
+            "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": n * (ROI * ROI + 5) * 4,
+                    "d2h_bytes_per_step": n * (5 + 3) * 4, "steps": e2e_steps, "host_memory": "pinned (dphlm_host_alloc)"},
+            "gpu_launches": args.steps,
+            "roofline": {
+                "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
+                "traffic": None, "kernel": "dphlm_fit_kernel<Gauss2D,MLE>", "kernel_ms": k_s * 1e3,
+                "peak_source": "SMs x 128 lanes x 2 x max SM clock (no fp32 entry in MEASURED_PEAKS.json)",
+                "flops_per_fit": float(np.mean(flops)) / n,
+                "hbm": {"achieved": BYTES_PER_FIT * n / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": BYTES_PER_FIT * n / k_s / 1e9 / hbm_peak, "bytes_per_fit": BYTES_PER_FIT,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"},
+            },
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count()
+            n_cpu = max(256, 40 * cores)
+            rate, popt_ref, info_ref, nfev_ref = cpu_reference(sets[0]["data"][:n_cpu], sets[0]["p0"][:n_cpu], cores)
+            r0 = step(0)
+            torch.cuda.synchronize()
+            from oracle.compare import parity_report
+
+            rep = parity_report("gauss2d", dict(popt=r0.popt[:n_cpu].cpu().numpy(), info=r0.info[:n_cpu].cpu().numpy(),
+                                                nfev=r0.nfev[:n_cpu].cpu().numpy()), dict(popt=popt_ref, info=info_ref, nfev=nfev_ref))
+            out["cpu_baseline"] = {"value": rate, "unit": "fits/s", "cores": cores, "kind": "port",
+                                   "sample": "first %d ROIs of input set 0, float64 oracle port of curve_fit(method='mle'), one process per core" % n_cpu,
+                                   "parity_on_sample": rep}
+        print(json.dumps(out))
+    for hd, hp, p1, p2 in h_sets:
+        del hd, hp
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,63 @@
+"""ctypes binding of the C ABI in ``include/dphlm.h`` (``dphtools_b200/csrc/libdphlm.so``).
+
+There is no CPU fallback: if the CUDA library has not been built, importing this module's ``lib()``
+raises, and so does every fit.
+"""
+
+import ctypes
+import os
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdphlm.so")
+
+SYMBOLS = [
+    "dphlm_desc_init", "dphlm_fit_batch", "dphlm_fit_batch_host", "dphlm_host_alloc", "dphlm_host_free",
+    "dphlm_device_count", "dphlm_version", "dphlm_last_error",
+]
+
+
+class Desc(ctypes.Structure):
+    """Mirror of ``struct dphlm_desc``."""
+
+    _fields_ = [
+        ("model", ctypes.c_int32), ("method", ctypes.c_int32), ("n_param", ctypes.c_int32),
+        ("dim0", ctypes.c_int32), ("dim1", ctypes.c_int32), ("group_lanes", ctypes.c_int32),
+        ("n_fits", ctypes.c_int64),
+        ("data", ctypes.c_void_p), ("xaxis", ctypes.c_void_p), ("p0", ctypes.c_void_p),
+        ("popt", ctypes.c_void_p), ("info", ctypes.c_void_p), ("nfev", ctypes.c_void_p), ("chisq", ctypes.c_void_p),
+        ("p_ls", ctypes.c_void_p), ("counts", ctypes.c_void_p),
+        ("ftol", ctypes.c_float), ("xtol", ctypes.c_float), ("gtol", ctypes.c_float), ("factor", ctypes.c_float),
+        ("maxfev", ctypes.c_int32), ("flags", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "dphtools_b200: the CUDA library %s has not been built (run `python -m dphtools_b200.build`); "
+                "there is no CPU fallback" % LIB_PATH
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        L.dphlm_desc_init.argtypes = [ctypes.POINTER(Desc)]
+        L.dphlm_desc_init.restype = None
+        L.dphlm_fit_batch.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p]
+        L.dphlm_fit_batch.restype = ctypes.c_int
+        L.dphlm_fit_batch_host.argtypes = [ctypes.POINTER(Desc), ctypes.c_int]
+        L.dphlm_fit_batch_host.restype = ctypes.c_int
+        L.dphlm_host_alloc.argtypes = [ctypes.c_size_t]
+        L.dphlm_host_alloc.restype = ctypes.c_void_p
+        L.dphlm_host_free.argtypes = [ctypes.c_void_p]
+        L.dphlm_host_free.restype = None
+        L.dphlm_device_count.restype = ctypes.c_int
+        L.dphlm_version.restype = ctypes.c_int
+        L.dphlm_last_error.restype = ctypes.c_char_p
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().dphlm_last_error().decode()

@@ -1,0 +1,267 @@
+"""Host-side mirror of ``dphtools.utils.lm`` for the B200 fitter.
+
+``curve_fit`` keeps the reference's signature, guards, return values and exceptions
+(``dphtools/utils/lm.py:510-685``); for ``method='ls'|'mle'`` the fit itself runs in the CUDA library
+through the C ABI of ``include/dphlm.h`` (no CPU fallback), which restricts ``f`` to the built-in models
+of :mod:`dphtools_b200.models`.  ``curve_fit_batch`` is the batched entry point the reference lacks:
+one call fits N independent ROIs.
+
+Per-fit ``info`` codes of the batched call are listed in ``include/dphlm.h``; the single-fit wrapper
+turns them back into the reference's exceptions.
+"""
+
+import ctypes
+import threading
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib, models
+
+FTOL = XTOL = 1.49012e-8
+
+BatchResult = namedtuple("BatchResult", "popt info nfev chisq p_ls counts")
+
+_MESSAGES = {  # dphtools/utils/lm.py:310-353 (taken over from scipy.optimize.leastsq)
+    1: "Both actual and predicted relative reductions in the sum of squares are at most {ftol}",
+    2: "The relative error between two consecutive iterates is at most {xtol}",
+    3: "Both actual and predicted relative reductions in the sum of squares\n  are at most {ftol:f} and the "
+       "relative error between two consecutive iterates is at \n  most {xtol:f}",
+    4: "The cosine of the angle between func(x) and any column of the\n  Jacobian is at most {gtol:f} in absolute value",
+    5: "Number of calls to function has reached maxfev = {maxfev:d}.",
+}
+
+
+def _resolve_model(model):
+    if isinstance(model, str):
+        if model not in models.BUILTIN:
+            raise ValueError("unknown built-in model %r (have %s)" % (model, sorted(models.BUILTIN)))
+        return models.BUILTIN[model]
+    if getattr(model, "model_id", None) is None:
+        raise NotImplementedError(
+            "method='ls'|'mle' runs on the GPU and supports only the built-in models of dphtools_b200.models "
+            "(gauss2d, gauss2d_elliptical, multi_exp); there is no CPU fallback for arbitrary callables"
+        )
+    return model
+
+
+def _is_torch(a):
+    return type(a).__module__.split(".")[0] == "torch"
+
+
+def _fill_desc(model, method, n_param, dim0, dim1, n_fits, ftol, xtol, gtol, maxfev, factor, group_lanes):
+    if method not in ("ls", "mle"):
+        raise TypeError("Method {} not recognized".format(method))
+    d = _lib.Desc()
+    _lib.lib().dphlm_desc_init(ctypes.byref(d))
+    d.model, d.method, d.n_param = model.model_id, 1 if method == "mle" else 0, n_param
+    d.dim0, d.dim1, d.n_fits, d.group_lanes = dim0, dim1, n_fits, group_lanes
+    d.ftol, d.xtol, d.gtol, d.factor = ftol, xtol, gtol, factor
+    d.maxfev = int(maxfev) if maxfev else 0
+    return d
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("dphlm: " + _lib.last_error())
+
+
+def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
+                    factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None):
+    """Fit ``N`` independent ROIs / histograms: the batched form of per-ROI
+    ``curve_fit(model, xdata, roi.ravel(), p0, jac=model.jac, method=method)`` (``lm.py:510-685``).
+
+    Parameters
+    ----------
+    model : built-in model callable or its name (``"gauss2d"``, ``"gauss2d_elliptical"``, ``"multi_exp"``)
+    data : ``[N, H, W]`` (2-D models) or ``[N, M]`` (``multi_exp``) float32.  A CUDA ``torch.Tensor`` is fitted
+        in place on its device and stream (asynchronously; results are CUDA tensors); a numpy array or CPU
+        tensor goes through the host entry point (copies overlap the kernels; results are numpy arrays).
+    p0 : ``[N, P]`` float32 initial guesses.
+    xdata : ``multi_exp`` only: the shared ``[M]`` x axis.
+    device : host path only: CUDA device index, or a list of indices to shard the batch over several
+        GPUs (contiguous shards, one host thread per device, no collective).
+
+    Returns ``BatchResult(popt[N,P], info[N], nfev[N], chisq[N], p_ls, counts)``; ``p_ls`` (result of the
+    least-squares pre-fit, ``lm.py:648``) and ``counts`` (``[N,4]``: pre-fit evaluations, accepted steps,
+    rejected steps, 0) are ``None`` unless requested.  The call never raises for an individual fit.
+    """
+    model = _resolve_model(model)
+    one_d = model.model_id == models.MODEL_MULTI_EXP
+    if _is_torch(data) and data.is_cuda:
+        return _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
+                           return_counts, group_lanes)
+    if _is_torch(data):
+        data = data.numpy()
+    if _is_torch(p0):
+        p0 = p0.cpu().numpy()
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    p0 = np.ascontiguousarray(p0, dtype=np.float32)
+    n = data.shape[0]
+    if data.ndim != (2 if one_d else 3) or p0.ndim != 2 or p0.shape[0] != n:
+        raise ValueError("data must be [N,%s] and p0 [N,P]" % ("M" if one_d else "H,W"))
+    n_param = p0.shape[1]
+    dim0, dim1 = (data.shape[1], 1) if one_d else data.shape[1:]
+    xa = None
+    if one_d:
+        if xdata is None:
+            raise ValueError("multi_exp needs xdata")
+        xa = np.ascontiguousarray(xdata, dtype=np.float32)
+        if xa.shape != (dim0,):
+            raise ValueError("xdata must have shape (M,)")
+    out = BatchResult(
+        np.empty((n, n_param), np.float32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32),
+        np.empty((n, n_param), np.float32) if return_stage1 else None, np.empty((n, 4), np.int32) if return_counts else None,
+    )
+    devices = [0] if device is None else ([device] if isinstance(device, int) else list(device))
+
+    def run(dev, lo, hi):
+        d = _fill_desc(model, method, n_param, dim0, dim1, hi - lo, ftol, xtol, gtol, maxfev, factor, group_lanes)
+        d.data, d.p0 = data[lo:hi].ctypes.data, p0[lo:hi].ctypes.data
+        d.xaxis = xa.ctypes.data if xa is not None else None
+        d.popt, d.info, d.nfev, d.chisq = (a[lo:hi].ctypes.data for a in out[:4])
+        d.p_ls = out.p_ls[lo:hi].ctypes.data if return_stage1 else None
+        d.counts = out.counts[lo:hi].ctypes.data if return_counts else None
+        return _lib.lib().dphlm_fit_batch_host(ctypes.byref(d), dev)
+
+    if len(devices) == 1:
+        _check(run(devices[0], 0, n))
+    else:  # contiguous shards, one host thread per device; ctypes releases the GIL
+        bounds = np.linspace(0, n, len(devices) + 1).astype(np.int64)
+        errs = []
+
+        def worker(i):
+            rc = run(devices[i], int(bounds[i]), int(bounds[i + 1]))
+            if rc:
+                errs.append(_lib.last_error())
+
+        threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(devices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise RuntimeError("dphlm: " + errs[0])
+    return out
+
+
+def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1, return_counts, group_lanes):
+    import torch
+
+    if data.dtype != torch.float32 or not data.is_contiguous():
+        data = data.contiguous().float()
+    p0 = torch.as_tensor(p0, dtype=torch.float32, device=data.device).contiguous()
+    n = data.shape[0]
+    if data.dim() != (2 if one_d else 3) or p0.dim() != 2 or p0.shape[0] != n:
+        raise ValueError("data must be [N,%s] and p0 [N,P]" % ("M" if one_d else "H,W"))
+    n_param = p0.shape[1]
+    dim0, dim1 = (data.shape[1], 1) if one_d else data.shape[1:]
+    xa = None
+    if one_d:
+        if xdata is None:
+            raise ValueError("multi_exp needs xdata")
+        xa = torch.as_tensor(xdata, dtype=torch.float32, device=data.device).contiguous()
+        if tuple(xa.shape) != (dim0,):
+            raise ValueError("xdata must have shape (M,)")
+    dev = data.device
+    popt = torch.empty((n, n_param), dtype=torch.float32, device=dev)
+    info = torch.empty(n, dtype=torch.int32, device=dev)
+    nfev = torch.empty(n, dtype=torch.int32, device=dev)
+    chisq = torch.empty(n, dtype=torch.float32, device=dev)
+    p_ls = torch.empty((n, n_param), dtype=torch.float32, device=dev) if return_stage1 else None
+    counts = torch.empty((n, 4), dtype=torch.int32, device=dev) if return_counts else None
+    d = _fill_desc(model, method, n_param, dim0, dim1, n, ftol, xtol, gtol, maxfev, factor, group_lanes)
+    d.data, d.p0, d.xaxis = data.data_ptr(), p0.data_ptr(), xa.data_ptr() if xa is not None else None
+    d.popt, d.info, d.nfev, d.chisq = popt.data_ptr(), info.data_ptr(), nfev.data_ptr(), chisq.data_ptr()
+    d.p_ls = p_ls.data_ptr() if return_stage1 else None
+    d.counts = counts.data_ptr() if return_counts else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _check(_lib.lib().dphlm_fit_batch(ctypes.byref(d), ctypes.c_void_p(stream)))
+    return BatchResult(popt, info, nfev, chisq, p_ls, counts)
+
+
+def _grid_shape(xdata):
+    """(h, w) if ``xdata`` is the (2, M) pixel grid of :func:`models.roi_grid`, else None."""
+    if xdata.ndim != 2 or xdata.shape[0] != 2:
+        return None
+    w, h = int(xdata[0].max()) + 1, int(xdata[1].max()) + 1
+    if h * w != xdata.shape[1] or not np.array_equal(xdata, models.roi_grid(h, w)):
+        return None
+    return h, w
+
+
+def curve_fit(f, xdata, ydata, p0=None, sigma=None, absolute_sigma=False, check_finite=True,
+              bounds=(-np.inf, np.inf), method=None, jac=None, **kwargs):
+    """Drop-in for ``dphtools.utils.lm.curve_fit`` (``lm.py:510-685``).
+
+    ``method`` in ``{None, 'lm', 'trf', 'dogbox'}`` delegates to :func:`scipy.optimize.curve_fit` exactly
+    as the reference does (``lm.py:606-619``).  ``method='ls'|'mle'`` runs the two-stage fit (least-squares
+    pre-fit, then the damped normal-equation loop with the Gaussian / Poisson estimator) on the GPU for the
+    built-in models; guards and exceptions follow ``lm.py:621-639, 651-662, 679-685``.
+    """
+    return_full = kwargs.pop("full_output", False)
+    if method in {"lm", "trf", "dogbox", None}:
+        import scipy.optimize
+
+        can_full_output = method not in {"trf", "dogbox"} and np.array_equal(bounds, (-np.inf, np.inf))
+        if can_full_output:
+            kwargs["full_output"] = return_full
+        res = scipy.optimize.curve_fit(f, xdata, ydata, p0, sigma, absolute_sigma, check_finite, bounds, method, jac, **kwargs)
+        if return_full and not can_full_output:
+            return res[0], res[1], None, "No error", 1
+        return res
+    if method not in ("ls", "mle"):
+        raise TypeError("Method {} not recognized".format(method))
+    if bounds != (-np.inf, np.inf):
+        raise NotImplementedError("Bounds has not been implemented")
+    if sigma is not None:
+        raise NotImplementedError("Weighting has not been implemented")
+    if jac is None:
+        raise NotImplementedError("You need a Jacobian")
+    model = _resolve_model(f)
+    unknown = set(kwargs) - {"ftol", "xtol", "gtol", "maxfev", "factor", "epsfcn", "diag", "col_deriv"}
+    if unknown:
+        raise TypeError("unexpected keyword arguments %s" % sorted(unknown))
+
+    ydata = np.asarray_chkfinite(ydata, dtype=float) if check_finite else np.asarray(ydata, dtype=float)
+    xdata = np.asarray_chkfinite(xdata, dtype=float) if check_finite else np.asarray(xdata, dtype=float)
+    if p0 is None:
+        if model.n_param is None:
+            raise ValueError("Unable to determine number of fit parameters.")
+        p0 = np.ones(model.n_param)
+    p0 = np.atleast_1d(np.asarray(p0, dtype=float))
+    if p0.size > ydata.size:
+        raise TypeError("Improper input: func input vector length N=%d must not exceed func output vector length M=%d" % (p0.size, ydata.size))
+    if model.model_id == models.MODEL_MULTI_EXP:
+        data, xa = ydata.reshape(1, -1), xdata.ravel()
+    else:
+        shape = _grid_shape(xdata)
+        if shape is None or shape[0] * shape[1] != ydata.size:
+            raise NotImplementedError("2-D models need xdata = models.roi_grid(h, w), the pixel grid of a row-major ROI")
+        data, xa = ydata.reshape((1,) + shape), None
+    ftol, xtol, gtol = kwargs.get("ftol", FTOL), kwargs.get("xtol", XTOL), kwargs.get("gtol", 0.0)
+    maxfev = kwargs.get("maxfev") or 100 * (p0.size + 1)
+    res = curve_fit_batch(model, data, p0[None], method, xa, ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev,
+                          factor=kwargs.get("factor", 100.0))
+    info, popt = int(res.info[0]), res.popt[0].astype(float)
+    fmt = dict(ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev)
+    if info == -100:
+        raise ValueError("array must not contain infs or NaNs")
+    if info < 0:  # the scipy pre-fit of the reference raises here (lm.py:642-644)
+        raise RuntimeError("Optimal parameters not found: " + _MESSAGES.get(-info, "pre-fit failed (ier=%d)" % -info).format(**fmt))
+    errmsg = _MESSAGES[info].format(**fmt)
+    # pcov = pinv(J^T J) from the SVD of the unweighted Jacobian (lm.py:672-677).  The reference uses J at the
+    # last accepted point; popt is at most one (converged, tiny) step away from it.
+    fjac = model.jac(xdata, *popt)
+    _, s, vt = np.linalg.svd(fjac, full_matrices=False)
+    keep = s > np.finfo(float).eps * max(fjac.shape) * s[0]
+    s, vt = s[keep], vt[: keep.sum()]
+    pcov = np.dot(vt.T / s**2, vt)
+    if info not in (1, 2, 3, 4):
+        raise RuntimeError("Optimal parameters not found: " + errmsg)
+    if return_full:
+        fvec = model(xdata, *popt)
+        fvec = np.where(fvec <= 0, 0.0, fvec) if method == "mle" else fvec - ydata
+        return popt, pcov, dict(fvec=fvec, fjac=fjac, nfev=int(res.nfev[0]), chisq=float(res.chisq[0])), errmsg, info
+    return popt, pcov

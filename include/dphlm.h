@@ -1,0 +1,84 @@
+/* dphlm.h -- C ABI of the B200 batched Levenberg-Marquardt / Poisson-MLE fitter.
+ *
+ * The reference (david-hoffman/dphtools) is pure Python and has no FFI layer; its boundary for this
+ * path is the Python call surface of dphtools/utils/lm.py.  Each entry point below names the reference
+ * interface it stands in for.  The Python host side (dphtools_b200/lm.py) binds these with ctypes; the
+ * stub a dphtools maintainer would add is shown in INTEGRATION.md.
+ *
+ * All functions are thread-safe and re-entrant across host threads that use distinct streams/devices.
+ * Return value: 0 on success, negative on error (text from dphlm_last_error(), thread-local).
+ */
+#ifndef DPHLM_H
+#define DPHLM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPHLM_VERSION 100
+
+/* model ids: callables a caller would pass as `f` to curve_fit (dphtools/utils/lm.py:510-512).
+ * MULTI_EXP is the reference's own model (dphtools/utils/fitfuncs.py:20-52); the Gaussians are new. */
+enum dphlm_model { DPHLM_GAUSS2D = 0, DPHLM_GAUSS2D_ELLIPTICAL = 1, DPHLM_MULTI_EXP = 2 };
+
+/* `method` of curve_fit / lm (dphtools/utils/lm.py:235, 519, 621-626) */
+enum dphlm_method { DPHLM_LS = 0, DPHLM_MLE = 1 };
+
+/* Per-fit `info` written by the fitter:
+ *    1, 2, 4   converged, same meaning as lm()'s info (dphtools/utils/lm.py:310-333, 409-432, 468-470)
+ *    5         stage 2 reached maxfev (lm.py:479-481); curve_fit raises RuntimeError (lm.py:679-680)
+ *   -k         the least-squares pre-fit (scipy curve_fit -> MINPACK lmder, lm.py:642-644) ended with
+ *              ier = k not in 1..4 (k = 5: maxfev); scipy raises RuntimeError there
+ *   -9         non-finite model value at p0
+ *   -100       non-finite input data; the reference raises ValueError (lm.py:651-662)            */
+
+typedef struct dphlm_desc {
+    int32_t model;       /* enum dphlm_model */
+    int32_t method;      /* enum dphlm_method */
+    int32_t n_param;     /* 5 (GAUSS2D), 7 (ELLIPTICAL), 2..7 (MULTI_EXP: 2 per exponential, +1 = offset) */
+    int32_t dim0, dim1;  /* ROI height, width; (n_bins, 1) for 1-D models */
+    int32_t group_lanes; /* lanes of a warp that own one fit: 0 = automatic, else 4, 8, 16 or 32 */
+    int64_t n_fits;
+    const float* data;   /* [n_fits, dim0, dim1] ydata, row-major                         (lm.py:512) */
+    const float* xaxis;  /* MULTI_EXP: [dim0] shared xdata; NULL for 2-D models (pixel indices)        */
+    const float* p0;     /* [n_fits, n_param] initial guesses                               (lm.py:514) */
+    float* popt;         /* [n_fits, n_param] fitted parameters                             (lm.py:682) */
+    int32_t* info;       /* [n_fits]                                                        (lm.py:669) */
+    int32_t* nfev;       /* [n_fits] infodict['nfev'] of stage 2                            (lm.py:489) */
+    float* chisq;        /* [n_fits] chi-square at popt (0.5 sum r^2, or Poisson deviance / 2)          */
+    float* p_ls;         /* optional [n_fits, n_param]: result of the least-squares pre-fit (lm.py:648) */
+    int32_t* counts;     /* optional [n_fits, 4]: pre-fit evaluations, accepted, rejected steps, 0      */
+    float ftol, xtol, gtol, factor; /* lm()/leastsq keywords, forwarded to both stages (lm.py:643, 668) */
+    int32_t maxfev;      /* <= 0: 100 * (n_param + 1)                                   (lm.py:306-307) */
+    int32_t flags;       /* reserved, 0 */
+} dphlm_desc;
+
+/* Fill the tolerances with the reference defaults (ftol = xtol = 1.49012e-8, gtol = 0, factor = 100,
+ * maxfev = 0 -> 100 (P + 1); dphtools/utils/lm.py:228-233) and zero everything else. */
+void dphlm_desc_init(dphlm_desc* d);
+
+/* Batched replacement for per-ROI curve_fit(f, xdata, ydata, p0, jac=..., method='ls'|'mle')
+ * (dphtools/utils/lm.py:510-685).  All pointers are DEVICE pointers on the current device; the work is
+ * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call returns without waiting. */
+int dphlm_fit_batch(const dphlm_desc* d, void* stream);
+
+/* Same contract with HOST pointers: copies the inputs to `device`, fits, copies the results back and
+ * returns when they are in place.  Large batches are cut into chunks whose copies overlap the kernels. */
+int dphlm_fit_batch_host(const dphlm_desc* d, int device);
+
+/* Page-locked host buffers for dphlm_fit_batch_host (plain malloc'ed memory works too, slower). */
+void* dphlm_host_alloc(size_t bytes);
+void dphlm_host_free(void* p);
+
+/* Useful-work accounting of the last dphlm_fit_batch_host / diagnostics */
+int dphlm_device_count(void);
+int dphlm_version(void);
+const char* dphlm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPHLM_H */

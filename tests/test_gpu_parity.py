@@ -1,0 +1,131 @@
+"""Parity of the CUDA path (through the C ABI) with the golden vectors minted from the live reference and
+with the float64 oracle.  Needs a B200: run with ``-m gpu``."""
+
+import numpy as np
+import pytest
+
+import dphtools_b200 as dph
+from dphtools_b200 import models, synth
+from oracle import lm_oracle
+from oracle.compare import parity_report
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+CASES = [
+    ("c1_mle", 0.99, 1.0), ("c2_mle", 0.995, 1.0), ("c2_ls", 0.99, 1.0), ("c3_mle", 0.995, 0.999),
+    ("c4_mle", 0.995, 1.0), ("c4_ls", 0.995, 1.0), ("c5_mle", 0.995, 1.0), ("c5_ls", 0.995, 1.0),
+]
+
+
+def _fit_gpu(g, group_lanes=0, host=False):
+    model = models.BUILTIN[g["model"]]
+    if host:
+        r = dph.curve_fit_batch(model, g["data"], g["p0"], g["method"], g["xaxis"], return_stage1=True, return_counts=True,
+                                group_lanes=group_lanes)
+        return dict(popt=r.popt, info=r.info, nfev=r.nfev, chisq=r.chisq, p_ls=r.p_ls, counts=r.counts)
+    r = dph.curve_fit_batch(model, torch.from_numpy(g["data"]).cuda(), torch.from_numpy(g["p0"]).cuda(), g["method"],
+                            g["xaxis"], return_stage1=True, return_counts=True, group_lanes=group_lanes)
+    torch.cuda.synchronize()
+    return {k: getattr(r, k).cpu().numpy() for k in ("popt", "info", "nfev", "chisq", "p_ls", "counts")}
+
+
+@pytest.mark.parametrize("name,min_info,min_within", CASES)
+def test_cuda_matches_reference_goldens(golden, name, min_info, min_within):
+    g = golden(name)
+    out = _fit_gpu(g)
+    rep = parity_report(g["model"], out, g)
+    print(name, rep)
+    assert rep["converged_equal"] == 1.0, rep
+    assert rep["info_equal"] >= min_info, rep
+    assert rep["within_rtol"] >= min_within, rep  # relative 1e-4 on amplitude, centre, width
+    ok = np.isfinite(g["p_ls"]).all(1)
+    rel = np.abs(out["p_ls"][ok] - g["p_ls"][ok]) / np.abs(g["p_ls"][ok])
+    assert np.quantile(rel.max(1), 0.99) < 1e-4
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+def test_every_group_size_gives_the_same_answers(golden, lanes):
+    g = golden("c3_mle")
+    out = _fit_gpu(g, group_lanes=lanes)
+    rep = parity_report(g["model"], out, g)
+    assert rep["converged_equal"] == 1.0 and rep["info_equal"] >= 0.995 and rep["within_rtol"] >= 0.999, rep
+
+
+def test_host_entry_point_equals_device_entry_point(golden):
+    g = golden("c2_mle")
+    a, b = _fit_gpu(g), _fit_gpu(g, host=True)
+    for k in ("popt", "info", "nfev", "chisq", "p_ls", "counts"):
+        np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_ragged_and_tiny_batches(golden):
+    g = golden("c2_mle")
+    full = _fit_gpu(g)
+    for n in (1, 2, 3, 5, 31, 33, 257):
+        sub = dict(g, data=g["data"][:n], p0=g["p0"][:n])
+        out = _fit_gpu(sub)
+        np.testing.assert_array_equal(out["popt"], full["popt"][:n])
+        np.testing.assert_array_equal(out["info"], full["info"][:n])
+    empty = dph.curve_fit_batch(models.gauss2d, torch.empty((0, 11, 11), device="cuda"), torch.empty((0, 5), device="cuda"), "mle")
+    assert empty.popt.shape == (0, 5)
+
+
+def test_bad_inputs_are_flagged_per_fit_not_raised(golden):
+    g = golden("c2_mle")
+    data = g["data"][:64].copy()
+    p0 = g["p0"][:64].copy()
+    data[3, 2, 2] = np.nan           # reference: ValueError from asarray_chkfinite (lm.py:651-652)
+    data[7, 0, 0] = np.inf
+    p0[11] = (0.0, 5.0, 5.0, 1.3, 0.0)  # zero amplitude: singular Jacobian columns
+    clean = _fit_gpu(dict(g, data=g["data"][:64], p0=g["p0"][:64]))
+    out = _fit_gpu(dict(g, data=data, p0=p0))
+    assert out["info"][3] == -100 and out["info"][7] == -100
+    keep = np.ones(64, bool)
+    keep[[3, 7, 11]] = False
+    np.testing.assert_array_equal(out["popt"][keep], clean["popt"][keep])
+    assert np.isfinite(out["popt"][keep]).all()
+
+
+def test_full_size_statistical_properties():
+    """BASELINE config 2 at full size (1e5 fits): every fit converges and recovers the truth within noise."""
+    w = synth.WORKLOADS["c2_gauss2d_11"](100000, seed=11)
+    r = dph.curve_fit_batch(models.gauss2d, torch.from_numpy(w["data"]).cuda(), torch.from_numpy(w["p0"]).cuda(), "mle")
+    torch.cuda.synchronize()
+    info, popt = r.info.cpu().numpy(), r.popt.cpu().numpy().astype(float)
+    assert ((info >= 1) & (info <= 4)).mean() > 0.9999
+    err = popt - w["truth"]
+    assert np.abs(np.median(err[:, 1:3], axis=0)).max() < 2e-3      # unbiased centre
+    assert np.median(np.abs(err[:, 1])) < 0.05                      # ~CRLB-level localisation precision
+    # idempotence: restarting from the answer stays there and converges immediately
+    r2 = dph.curve_fit_batch(models.gauss2d, torch.from_numpy(w["data"]).cuda(), r.popt, "mle")
+    torch.cuda.synchronize()
+    p2 = r2.popt.cpu().numpy().astype(float)
+    ok = (info >= 1) & (info <= 4)
+    assert np.quantile(np.abs(p2[ok] - popt[ok]).max(1) / np.abs(popt[ok]).max(1), 0.999) < 1e-4
+    # a fresh oracle run on a slice of the same batch
+    n = 200
+    ref = lm_oracle.fit_batch(models.gauss2d, w["data"][:n], w["p0"][:n], "mle", models.roi_grid(11, 11))
+    rep = parity_report("gauss2d", dict(popt=popt[:n], info=info[:n], nfev=r.nfev.cpu().numpy()[:n]), ref)
+    assert rep["converged_equal"] == 1.0 and rep["within_rtol"] == 1.0, rep
+
+
+def test_single_fit_curve_fit_surface(golden):
+    g = golden("c1_mle")
+    xy = models.roi_grid(15, 15)
+    y = g["data"][0].ravel().astype(float)
+    popt, pcov, infodict, errmsg, info = dph.curve_fit(models.gauss2d, xy, y, g["p0"][0].astype(float), jac=models.gauss2d_jac,
+                                                       method="mle", full_output=True)
+    ref_popt, ref_pcov, ref_infod, ref_info, _ = lm_oracle.curve_fit(
+        models.gauss2d, xy, y, g["p0"][0].astype(float), models.gauss2d_jac, "mle", full_output=True, return_stage1=True)
+    assert info == ref_info
+    np.testing.assert_allclose(popt, ref_popt, rtol=1e-4)
+    np.testing.assert_allclose(pcov, ref_pcov, rtol=1e-3)
+    assert infodict["fvec"].shape == (225,) and infodict["fjac"].shape == (225, 5)
+    with pytest.raises(RuntimeError, match="Optimal parameters not found"):
+        dph.curve_fit(models.gauss2d, xy, y, g["p0"][0].astype(float), jac=models.gauss2d_jac, method="mle", maxfev=2)
+    # the reference's own test case through method='ls' (multi_exp, tests/test_fitfuncs.py:32-36)
+    x = np.linspace(0, 10)
+    popt, _ = dph.curve_fit(models.multi_exp, x, models.multi_exp(x, 10, 3, 5), p0=(8.0, 2.0, 4.0), jac=models.multi_exp_jac, method="ls")
+    np.testing.assert_allclose(popt, (10, 3, 5), rtol=1e-3)
