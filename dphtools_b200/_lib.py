@@ -7,7 +7,7 @@ raises, and so does every fit.
 import ctypes
 import os
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdphlm.so")
+LIB_PATH = os.environ.get("DPHLM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdphlm.so")
 
 SYMBOLS = [
     "dphlm_desc_init", "dphlm_fit_batch", "dphlm_fit_batch_host", "dphlm_host_alloc", "dphlm_host_free",

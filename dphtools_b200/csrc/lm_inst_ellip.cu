@@ -1,0 +1,5 @@
+// explicit instantiations: rotated elliptical 2-D Gaussian
+#include "lm_launch.cuh"
+namespace dphlm {
+int launch_gauss2d_elliptical(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s) { DPH_DISPATCH_G(Gauss2DElliptical, G, mle, a, ctx, s); }
+}  // namespace dphlm

@@ -1,0 +1,5 @@
+// explicit instantiations: symmetric 2-D Gaussian
+#include "lm_launch.cuh"
+namespace dphlm {
+int launch_gauss2d(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s) { DPH_DISPATCH_G(Gauss2D, G, mle, a, ctx, s); }
+}  // namespace dphlm

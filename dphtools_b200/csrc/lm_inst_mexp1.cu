@@ -1,0 +1,10 @@
+// explicit instantiations: sum of 1 exponential(s), with and without offset
+#include "lm_launch.cuh"
+namespace dphlm {
+int launch_multi_exp1(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s) {
+    using M0 = MultiExp<1, false>;
+    using M1 = MultiExp<1, true>;
+    if (offset) { DPH_DISPATCH_G(M1, G, mle, a, ctx, s); }
+    DPH_DISPATCH_G(M0, G, mle, a, ctx, s);
+}
+}  // namespace dphlm
