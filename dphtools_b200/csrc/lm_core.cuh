@@ -330,25 +330,26 @@ struct MultiExp {
 
 // ------------------------------------------------------------------------------ lane group / storage
 // Per-fit pixel state, pointer based so that the device (shared memory) and host builds share code.
-//   y[M]          data (MLE: already clamped to >= 0)
-//   e[2][NE][M]   stored exponentials, double buffered: `cur` is the accepted point, 1-cur the trial
-//   cxy[M]        pixel coordinates (x, y), shared by all fits
+//   y[M]               data (MLE: already clamped to >= 0)
+//   e[2][NE][stride]   stored exponentials, double buffered: `cur` is the accepted point, 1-cur the trial
+//   cxy[M]             pixel coordinates (x, y), shared by all fits
 struct Coord { float x, y; };
 
 template <int NE>
 struct PixelState {
     float* y;
-    float* e;  // [2][NE][M]
+    float* e;  // [2][NE][stride]
     const Coord* cxy;
-    int M;
+    int M, stride;
     int cur;
-    DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * M; }
+    DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * stride; }
 };
 
 // Group of G lanes.  On the host G == 1 and the reductions are the identity.
 template <int G>
 struct Lanes {
-    int lane;  // index inside the group
+    int lane;        // index inside the group
+    unsigned gmask;  // the warp lanes of this group
 #if defined(__CUDA_ARCH__)
     DPH_HD float sum(float v) const {
 #pragma unroll
@@ -374,19 +375,31 @@ struct Lanes {
 };
 
 // ------------------------------------------------------------------------------------ pixel passes
+constexpr int kFlagNonFinite = 1, kFlagPredNeg = 2, kFlagIrregular = 4;
+
 template <int P>
-struct Normal {  // per-lane partial sums of one pass
+struct Normal {  // per-lane partial sums of one pass, group totals after the reduction
     float A[NT<P>::value];
     float g[P];
     float actual, predicted;  // chi2(old) - chi2(trial), chi2(old) - chi2(trial + J_old d)
-    int flags;                // bit0: non-finite model value, bit1: predicted model < 0 somewhere
+    float chi1;               // chi2(trial) itself (LS: always; MLE: only when asked for)
+    int flags;
     DPH_HD void clear() {
 #pragma unroll
         for (int i = 0; i < NT<P>::value; ++i) A[i] = 0.0f;
 #pragma unroll
         for (int i = 0; i < P; ++i) g[i] = 0.0f;
-        actual = predicted = 0.0f;
+        actual = predicted = chi1 = 0.0f;
         flags = 0;
+    }
+    template <int G>
+    DPH_HD void reduce(const Lanes<G>& ln) {
+        ln.template sum_all<NT<P>::value>(A);
+        ln.template sum_all<P>(g);
+        actual = ln.sum(actual);
+        predicted = ln.sum(predicted);
+        chi1 = ln.sum(chi1);
+        flags = ln.any(flags);
     }
 };
 
@@ -418,129 +431,107 @@ DPH_HD void mle_weights(float f, float y, float& w, float& res) {
     res = ok ? 1.0f - yf : 1.0f;
 }
 
-// First evaluation at a point: stores the exponentials in buffer `cur`, accumulates A, g and the
-// chi-square itself (directly; only needed to ~1e-6 relative for the ftol right-hand sides).
-template <class Mo, bool MLE, int G>
-DPH_HD void init_pass(const Lanes<G>& ln, PixelState<Mo::NE>& px, const typename Mo::Par& q, Normal<Mo::P>& n, float& chisq) {
-    constexpr int P = Mo::P;
+// Evaluation at the trial point q1 = q0 + d.  Reads the exponentials of the accepted point (buffer
+// cur), writes the trial ones (buffer 1-cur), accumulates the chi-square reductions from per-pixel
+// differences and, speculatively, A and g at the trial point.  QUIRK (lm.py:446-449): the predicted
+// model is f(x_new) + J(x_old) d.  With `init` the accepted point does not exist yet: the pass is run
+// with d = 0 and the old exponentials are taken equal to the new ones (actual = predicted = 0).
+//
+// FAST is the branch-free version for the regular case (all model values > 0, finite); a group that
+// meets anything else raises kFlagIrregular and the caller repeats the pass with FAST = false, which
+// implements the reference's clamps and zeroing rules literally.
+template <class Mo, bool MLE, bool PRED, bool FAST, int G>
+DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const typename Mo::Par& q0,
+                       const typename Mo::Par& q1, const typename Mo::Step& st, bool init, bool want_chi,
+                       Normal<Mo::P>& n) {
+    constexpr int P = Mo::P, NE = Mo::NE;
     n.clear();
-    float chi = 0.0f;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 2
-#endif
-    for (int i = ln.lane; i < px.M; i += G) {
-        typename Mo::Geo geo;
-        float e[Mo::NE], J[P];
-        Mo::geometry(q, px.cxy[i].x, px.cxy[i].y, geo);
-        Mo::expo(q, geo, e);
+    const float* e0p[NE];
+    float* e1p[NE];
 #pragma unroll
-        for (int j = 0; j < Mo::NE; ++j) px.ebuf(px.cur, j)[i] = e[j];
-        float f = Mo::value(q, e);
-        float y = px.y[i];
-        if (!f_finite(f)) n.flags |= 1;
-        Mo::jac(q, geo, e, J);
-        if (MLE) {
-            f = clamp_nonneg(f);
-            float w, res;
-            mle_weights(f, y, w, res);
-            accumulate<P>(n, J, w, res);
-            chi += mle_term_direct(f, y) - y;
-        } else {
-            float r = f - y;
-            accumulate<P>(n, J, 1.0f, r);
-            chi = f_fma(0.5f * r, r, chi);
-        }
-    }
-    ln.template sum_all<NT<P>::value>(n.A);
-    ln.template sum_all<P>(n.g);
-    chisq = ln.sum(chi);
-    n.flags = ln.any(n.flags);
-}
-
-// Trial evaluation at q1 = q0 + d.  Reads the exponentials of the accepted point (buffer cur), writes
-// the trial ones (buffer 1-cur), accumulates the chi-square reductions from per-pixel differences and,
-// speculatively, A and g at the trial point.  QUIRK (lm.py:446-449): the predicted model is
-// f(x_new) + J(x_old) d.
-template <class Mo, bool MLE, bool PRED, int G>
-DPH_HD void trial_pass(const Lanes<G>& ln, PixelState<Mo::NE>& px, const typename Mo::Par& q0, const typename Mo::Par& q1,
-                       const typename Mo::Step& st, Normal<Mo::P>& n) {
-    constexpr int P = Mo::P;
-    n.clear();
+    for (int j = 0; j < NE; ++j) { e0p[j] = px.ebuf(px.cur, j); e1p[j] = px.ebuf(1 - px.cur, j); }
+    const float* ys = px.y;
+    const Coord* cxy = px.cxy;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
 #endif
     for (int i = ln.lane; i < px.M; i += G) {
         typename Mo::Geo g0, g1;
-        float e0[Mo::NE], e1[Mo::NE], J[P];
-        float cx = px.cxy[i].x, cy = px.cxy[i].y;
-        Mo::geometry(q0, cx, cy, g0);
-        Mo::geometry(q1, cx, cy, g1);
-#pragma unroll
-        for (int j = 0; j < Mo::NE; ++j) e0[j] = px.ebuf(px.cur, j)[i];
+        float e0[NE], e1[NE], J[P];
+        const Coord c = cxy[i];
+        Mo::geometry(q0, c.x, c.y, g0);
+        Mo::geometry(q1, c.x, c.y, g1);
         Mo::expo(q1, g1, e1);
 #pragma unroll
-        for (int j = 0; j < Mo::NE; ++j) px.ebuf(1 - px.cur, j)[i] = e1[j];
-        float y = px.y[i];
-        float f0 = Mo::value(q0, e0);
-        float f1 = Mo::value(q1, e1);
-        if (!f_finite(f1)) n.flags |= 1;
-        float dl = Mo::delta(q0, st, g0, e0, e1);
+        for (int j = 0; j < NE; ++j) {
+            float t = e0p[j][i];
+            e0[j] = init ? e1[j] : t;
+            e1p[j][i] = e1[j];
+        }
+        const float y = ys[i];
+        const float f0 = Mo::value(q0, e0);
+        const float f1 = Mo::value(q1, e1);
+        const float dl = Mo::delta(q0, st, g0, e0, e1);
         Mo::jac(q1, g1, e1, J);
         if (MLE) {
-            float f0c = clamp_nonneg(f0), f1c = clamp_nonneg(f1);
-            float rf0 = f_rcp(f0c);
-            bool reg = (f0c > 0.0f) && (f1c > 0.0f);
-            if (reg) {
+            if (FAST) {
+                const float f0c = fmaxf(f0, 0.0f), f1c = fmaxf(f1, 0.0f);
+                const float rf0 = f_rcp(f0c);
                 n.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
-            } else {
-                n.actual += mle_term_direct(f0c, y) - mle_term_direct(f1c, y);
-            }
-            if (PRED) {
-                float jd = Mo::jdx(q0, st, g0, e0);
-                float fp = f1c + jd;
-                if (fp < 0.0f) n.flags |= 2;
-                if (reg && fp > 0.0f) {
-                    float dp = dl + jd;
+                float lo = fminf(f0c, f1c);
+                if (PRED) {
+                    const float jd = Mo::jdx(q0, st, g0, e0);
+                    const float dp = dl + jd;
+                    lo = fminf(lo, f1c + jd);
                     n.predicted += f_fma(y, log1p_acc(dp * rf0), -dp);
-                } else {
-                    n.predicted += mle_term_direct(f0c, y) - mle_term_direct(fp, y);
                 }
+                if (!(lo > 0.0f)) n.flags |= kFlagIrregular;
+                const float rf1 = f_rcp(f1c);
+                const float yf = y * rf1;
+                accumulate<P>(n, J, yf * rf1, 1.0f - yf);
+                if (want_chi) n.chi1 += mle_term_direct(f1c, y) - y;
+            } else {
+                if (!f_finite(f1)) n.flags |= kFlagNonFinite;
+                const float f0c = clamp_nonneg(f0), f1c = clamp_nonneg(f1);
+                const float rf0 = f_rcp(f0c);
+                const bool reg = (f0c > 0.0f) && (f1c > 0.0f);
+                if (reg) n.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
+                else n.actual += mle_term_direct(f0c, y) - mle_term_direct(f1c, y);
+                if (PRED) {
+                    const float jd = Mo::jdx(q0, st, g0, e0);
+                    const float fp = f1c + jd;
+                    if (fp < 0.0f) n.flags |= kFlagPredNeg;
+                    if (reg && fp > 0.0f) {
+                        const float dp = dl + jd;
+                        n.predicted += f_fma(y, log1p_acc(dp * rf0), -dp);
+                    } else {
+                        n.predicted += mle_term_direct(f0c, y) - mle_term_direct(fp, y);
+                    }
+                }
+                float w, res;
+                mle_weights(f1c, y, w, res);
+                accumulate<P>(n, J, w, res);
+                if (want_chi) n.chi1 += mle_term_direct(f1c, y) - y;
             }
-            float w, res;
-            mle_weights(f1c, y, w, res);
-            accumulate<P>(n, J, w, res);
         } else {
-            float r0 = f0 - y;
+            const float r0 = f0 - y, r1 = f1 - y;
             n.actual = f_fma(-dl, f_fma(0.5f, dl, r0), n.actual);
             if (PRED) {
-                float dp = dl + Mo::jdx(q0, st, g0, e0);
+                const float dp = dl + Mo::jdx(q0, st, g0, e0);
                 n.predicted = f_fma(-dp, f_fma(0.5f, dp, r0), n.predicted);
             }
-            accumulate<P>(n, J, 1.0f, f1 - y);
+            n.chi1 = f_fma(0.5f * r1, r1, n.chi1);
+            accumulate<P>(n, J, 1.0f, r1);
         }
     }
-    ln.template sum_all<NT<P>::value>(n.A);
-    ln.template sum_all<P>(n.g);
-    n.actual = ln.sum(n.actual);
-    if (PRED) n.predicted = ln.sum(n.predicted);
-    n.flags = ln.any(n.flags);
+    n.reduce(ln);
+    if (!MLE && !f_finite(n.chi1)) n.flags |= kFlagNonFinite;
 }
 
 // ------------------------------------------------------------------------------------- options/result
 struct Options {
     float ftol, xtol, gtol, factor;
     int maxfev;  // <= 0: 100 * (P + 1)
-};
-
-template <int P>
-struct FitResult {
-    float x[P];
-    float p_ls[P];
-    float chisq;
-    int info;      // stage B exit (lm.py): 1, 2, 4, 5; -ier when the stage-A pre-fit ends with ier not in 1..4
-    int nfev;      // stage B: zero-based index of the last trip (lm.py:489)
-    int nfev_ls;   // stage A: function evaluations (MINPACK nfev)
-    int n_acc, n_rej;
 };
 
 // ------------------------------------------------------------------------- stage A: MINPACK lmder
@@ -557,7 +548,7 @@ DPH_HD void lmpar_normal(const float* A, const float* g, const float* D, float d
         float s = 0.0f;
 #pragma unroll
         for (int i = 0; i < P; ++i) s = f_fma(D[i] * p[i], p[i], s);
-        dxnorm = sqrtf(s);
+        dxnorm = f_sqrt(s);
         fp = dxnorm - delta;
         if (fp <= 0.1f * delta) { par = 0.0f; pnorm = dxnorm; return; }
     } else {
@@ -565,21 +556,21 @@ DPH_HD void lmpar_normal(const float* A, const float* g, const float* D, float d
     }
     float parl = 0.0f;
     if (full_rank) {
-        float rdx = 1.0f / dxnorm;
+        float rdx = f_rcp(dxnorm);
 #pragma unroll
         for (int i = 0; i < P; ++i) w[i] = D[i] * p[i] * rdx;
         float t2 = chol_forward<P>(U, w, z);
-        parl = (fp / delta) / t2;
+        parl = fp * f_rcp(delta * t2);
     }
     float gn = 0.0f;
 #pragma unroll
-    for (int i = 0; i < P; ++i) gn = f_fma(g[i] * g[i], 1.0f / D[i], gn);
-    float gnorm = sqrtf(gn);
-    float paru = gnorm / delta;
+    for (int i = 0; i < P; ++i) gn = f_fma(g[i] * g[i], f_rcp(D[i]), gn);
+    float gnorm = f_sqrt(gn);
+    float paru = gnorm * f_rcp(delta);
     if (paru == 0.0f) paru = dwarf / fminf(delta, 0.1f);
     par = fmaxf(par, parl);
     par = fminf(par, paru);
-    if (par == 0.0f) par = full_rank ? gnorm / dxnorm : 0.0f;
+    if (par == 0.0f) par = full_rank ? gnorm * f_rcp(dxnorm) : 0.0f;
     for (int it = 1;; ++it) {
         if (par == 0.0f) par = fmaxf(dwarf, 0.001f * paru);
         bool ok = chol_factor<P>(A, D, par, U);
@@ -587,7 +578,7 @@ DPH_HD void lmpar_normal(const float* A, const float* g, const float* D, float d
         float s = 0.0f;
 #pragma unroll
         for (int i = 0; i < P; ++i) s = f_fma(D[i] * p[i], p[i], s);
-        dxnorm = sqrtf(s);
+        dxnorm = f_sqrt(s);
         float temp = fp;
         fp = dxnorm - delta;
         if (!ok || !f_finite(fp)) {  // not factorizable in fp32: push par up and retry (bounded by it == 10)
@@ -598,11 +589,11 @@ DPH_HD void lmpar_normal(const float* A, const float* g, const float* D, float d
             continue;
         }
         if (fabsf(fp) <= 0.1f * delta || (parl == 0.0f && fp <= temp && temp < 0.0f) || it == 10) break;
-        float rdx = 1.0f / dxnorm;
+        float rdx = f_rcp(dxnorm);
 #pragma unroll
         for (int i = 0; i < P; ++i) w[i] = D[i] * p[i] * rdx;
         float t2 = chol_forward<P>(U, w, z);
-        float parc = (fp / delta) / t2;
+        float parc = fp * f_rcp(delta * t2);
         if (fp > 0.0f) parl = fmaxf(parl, par);
         if (fp < 0.0f) paru = fminf(paru, par);
         par = fmaxf(parl, par + parc);
@@ -610,238 +601,301 @@ DPH_HD void lmpar_normal(const float* A, const float* g, const float* D, float d
     pnorm = dxnorm;
 }
 
-// ------------------------------------------------------------------------------------- one fit
-// Runs both stages for the fit owned by this lane group.  `active` is false for padding groups of a
-// partially filled warp: they execute the same instruction stream (the shuffles are warp-wide) but
-// their state is never written back.
-template <class Mo, bool MLE, int G>
-DPH_HD void fit_one(const Lanes<G>& ln, PixelState<Mo::NE>& px, const float* p0, const Options& opt, bool active,
-                    FitResult<Mo::P>& out) {
-    constexpr int P = Mo::P;
-    constexpr int NTP = NT<P>::value;
-    const int maxfev = opt.maxfev > 0 ? opt.maxfev : 100 * (P + 1);
 
-    float x[P], A[NTP], g[P], D[P], p[P];
-    typename Mo::Par q0, q1;
-    typename Mo::Step st;
-    Normal<P> nrm;
-#pragma unroll
-    for (int i = 0; i < P; ++i) x[i] = p0[i];
-
-    // ================================ stage A: least-squares pre-fit (MINPACK lmder, lm.py:642-648)
-    px.cur = 0;
-    Mo::prepare(x, q0);
+// Per-fit state of the least-squares pre-fit: MINPACK lmder (notebooks/lmder.f:186-452) over the normal
+// equations.  One trip of the driver = propose() a step, one trial pass, consume() its sums.
+template <class Mo>
+struct StageA {
+    static constexpr int P = Mo::P;
+    static constexpr int NTP = NT<P>::value;
+    static constexpr bool kMle = false, kPred = false;
+    float x[P], A[NTP], g[P], D[P];
+    typename Mo::Par q0;
     float chi;  // 0.5 * fnorm^2
-    init_pass<Mo, false, G>(ln, px, q0, nrm, chi);
-#pragma unroll
-    for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
-#pragma unroll
-    for (int i = 0; i < P; ++i) g[i] = nrm.g[i];
-    int ier = 0;
-    if (nrm.flags & 1) ier = 9;  // non-finite start (scipy raises ValueError)
-    int nfev_ls = 1;
-    float par = 0.0f, delta = 0.0f, xnorm = 0.0f;
-    bool first = true;
-    bool running = active && ier == 0;
-    bool fresh = true;  // A, g belong to a newly accepted point: rescale (lmder.f:319-321)
-    while (Lanes<G>::warp_any(running)) {
-        float pnorm = 0.0f;
-        if (running) {
-            if (fresh) {
-                if (first) {
-#pragma unroll
-                    for (int i = 0; i < P; ++i) D[i] = A[tri<P>(i, i)] == 0.0f ? 1.0f : A[tri<P>(i, i)];
-                    float s = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < P; ++i) s = f_fma(D[i] * x[i], x[i], s);
-                    xnorm = sqrtf(s);
-                    delta = opt.factor * xnorm;
-                    if (delta == 0.0f) delta = opt.factor;
-                }
-                if (opt.gtol > 0.0f && chi > 0.0f) {  // lmder.f gnorm test
-                    float gnorm = 0.0f, rf = 1.0f / sqrtf(2.0f * chi);
-#pragma unroll
-                    for (int i = 0; i < P; ++i)
-                        if (A[tri<P>(i, i)] != 0.0f) gnorm = fmaxf(gnorm, fabsf(g[i] * rf / sqrtf(A[tri<P>(i, i)])));
-                    if (gnorm <= opt.gtol) ier = 4;
-                }
-#pragma unroll
-                for (int i = 0; i < P; ++i) D[i] = fmaxf(D[i], A[tri<P>(i, i)]);
-                fresh = false;
-            }
-            if (ier == 0) {
-                lmpar_normal<P>(A, g, D, delta, par, p, pnorm);
-                if (first) delta = fminf(delta, pnorm);
-            } else {
-                running = false;
-            }
-        }
-        if (!running) {
-#pragma unroll
-            for (int i = 0; i < P; ++i) p[i] = 0.0f;
-        }
-        float xn[P];
-#pragma unroll
-        for (int i = 0; i < P; ++i) xn[i] = x[i] + p[i];
-        Mo::prepare(xn, q1);
-        Mo::prepare_step(q0, q1, p, st);
-        trial_pass<Mo, false, false, G>(ln, px, q0, q1, st, nrm);
-        if (running) {
-            ++nfev_ls;
-            float fn2 = 2.0f * chi;                 // fnorm^2
-            float actual = nrm.actual;
-            bool bad = (nrm.flags & 1) || !f_finite(actual);
-            // actred = 1 - (fnorm1/fnorm)^2 unless 0.1 fnorm1 >= fnorm  (lmder.f: actred = -1)
-            float actred = (!bad && (fn2 - 2.0f * actual) < 100.0f * fn2) ? 2.0f * actual / fn2 : -1.0f;
-            float t1 = quad_form<P>(A, p) / fn2;
-            float t2 = par * pnorm * pnorm / fn2;
-            float prered = t1 + 2.0f * t2;
-            float dirder = -(t1 + t2);
-            float ratio = prered != 0.0f ? actred / prered : 0.0f;
-            if (ratio <= 0.25f) {
-                float temp = actred >= 0.0f ? 0.5f : 0.5f * dirder / (dirder + 0.5f * actred);
-                if (bad || (fn2 - 2.0f * actual) >= 100.0f * fn2 || temp < 0.1f) temp = 0.1f;
-                delta = temp * fminf(delta, pnorm * 10.0f);
-                par = par / temp;
-            } else if (par == 0.0f || ratio >= 0.75f) {
-                delta = 2.0f * pnorm;
-                par = 0.5f * par;
-            }
-            if (ratio >= 1e-4f) {  // successful iteration
-#pragma unroll
-                for (int i = 0; i < P; ++i) x[i] = xn[i];
-                q0 = q1;
-                px.cur = 1 - px.cur;
-#pragma unroll
-                for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
-#pragma unroll
-                for (int i = 0; i < P; ++i) g[i] = nrm.g[i];
-                float s = 0.0f;
-#pragma unroll
-                for (int i = 0; i < P; ++i) s = f_fma(D[i] * x[i], x[i], s);
-                xnorm = sqrtf(s);
-                chi -= actual;
-                fresh = true;
-                first = false;
-            }
-            bool fconv = fabsf(actred) <= opt.ftol && prered <= opt.ftol && 0.5f * ratio <= 1.0f;
-            if (fconv) ier = 1;
-            if (delta <= opt.xtol * xnorm) ier = fconv ? 3 : 2;
-            if (ier == 0 && nfev_ls >= maxfev) ier = 5;
-            if (ier == 0 && !(delta > 0.0f)) ier = 7;
-            if (ier != 0) running = false;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < P; ++i) out.p_ls[i] = x[i];
-    out.nfev_ls = nfev_ls;
+    float par, delta, xnorm, pnorm;
+    int ier, nfev;
+    bool init, first;
 
-    // ================================ stage B: the reference's lm() loop (lm.py:389-481)
-    bool okA = active && ier >= 1 && ier <= 4;
-    float dtd[P];
-    float chisq_old, lam;
-    Mo::prepare(x, q0);
-    init_pass<Mo, MLE, G>(ln, px, q0, nrm, chisq_old);
+    DPH_HD void start(const float* p0) {
 #pragma unroll
-    for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
-#pragma unroll
-    for (int i = 0; i < P; ++i) { g[i] = nrm.g[i]; dtd[i] = A[tri<P>(i, i)]; }
-    {
-        float s = 0.0f;
-#pragma unroll
-        for (int i = 0; i < P; ++i) s = f_fma(dtd[i] * x[i], x[i], s);
-        lam = sqrtf(s);                                            // lm.py:398
-        if (!(lam > 0.0f) || !f_finite(lam)) lam = 100.0f;         // lm.py:399-400
+        for (int i = 0; i < P; ++i) x[i] = p0[i];
+        Mo::prepare(x, q0);
+        par = delta = xnorm = pnorm = chi = 0.0f;
+        ier = 0; nfev = 0;
+        init = true; first = true;
     }
-    float xret[P];
-#pragma unroll
-    for (int i = 0; i < P; ++i) xret[i] = x[i];
-    float chisq_ret = chisq_old;
-    int info = 5, ev = 0, n_acc = 0, n_rej = 0;
-    running = okA;
-    if (maxfev <= 0) running = false;
-    float U[NTP];
-    while (Lanes<G>::warp_any(running)) {
-        bool live = false;
-        if (running) {
-            if (opt.gtol > 0.0f) {  // lm.py:358-363, 409-411
-                float gm = 0.0f;
-#pragma unroll
-                for (int i = 0; i < P; ++i) gm = fmaxf(gm, fabsf(g[i]));
-                if (gm <= opt.gtol) { info = 4; running = false; }
-            }
-        }
-        if (running) {
-            bool ok = chol_factor<P>(A, dtd, lam, U);
-            if (ok) {
-                chol_solve_neg<P>(U, g, p);
-#pragma unroll
-                for (int i = 0; i < P; ++i) ok = ok && f_finite(p[i]);
-            }
-            if (!ok) {
-                lam *= opt.factor;  // lm.py:426-428: the trip is consumed
-            } else {
-                float dn = 0.0f, xn2 = 0.0f;
-#pragma unroll
-                for (int i = 0; i < P; ++i) { dn = f_fma(p[i], p[i], dn); xn2 = f_fma(x[i], x[i], xn2); }
-                if (sqrtf(dn) <= opt.xtol * (sqrtf(xn2) + opt.xtol)) {  // lm.py:365-367, 430-432
-                    info = 2; running = false;
-                } else {
-                    live = true;
-                }
-            }
-        }
-        if (!live) {
+    DPH_HD bool wants_chi() const { return false; }
+    // returns false when the fit ended without needing the pass
+    DPH_HD bool propose(const Options&, float* p) {
+        if (init) {
 #pragma unroll
             for (int i = 0; i < P; ++i) p[i] = 0.0f;
+            return true;
         }
-        float xn[P];
+        lmpar_normal<P>(A, g, D, delta, par, p, pnorm);
+        if (first) delta = fminf(delta, pnorm);
+        return true;
+    }
+    // new Jacobian at an accepted point: gradient test and rescaling (lmder.f: gnorm, diag = max(diag, wa2))
+    DPH_HD void fresh(const Options& opt) {
+        if (opt.gtol > 0.0f && chi > 0.0f) {
+            float gnorm = 0.0f, rf = f_rsqrt(2.0f * chi);
 #pragma unroll
-        for (int i = 0; i < P; ++i) xn[i] = x[i] + p[i];
-        Mo::prepare(xn, q1);
-        Mo::prepare_step(q0, q1, p, st);
-        trial_pass<Mo, MLE, true, G>(ln, px, q0, q1, st, nrm);
+            for (int i = 0; i < P; ++i)
+                if (A[tri<P>(i, i)] != 0.0f) gnorm = fmaxf(gnorm, fabsf(g[i] * rf * f_rsqrt(A[tri<P>(i, i)])));
+            if (gnorm <= opt.gtol) ier = 4;
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) D[i] = fmaxf(D[i], A[tri<P>(i, i)]);
+    }
+    // returns true when the fit is finished; `accepted` tells the driver to flip the exponential buffers
+    DPH_HD bool consume(const Options& opt, const Normal<P>& n, const float* p, const typename Mo::Par& q1, bool& accepted) {
+        const int maxfev = opt.maxfev > 0 ? opt.maxfev : 100 * (P + 1);
+        accepted = false;
+        if (init) {
+            init = false;
+            nfev = 1;
+            if (n.flags & kFlagNonFinite) { ier = 9; return true; }  // scipy raises ValueError on a non-finite start
+#pragma unroll
+            for (int i = 0; i < NTP; ++i) A[i] = n.A[i];
+#pragma unroll
+            for (int i = 0; i < P; ++i) g[i] = n.g[i];
+            chi = n.chi1;
+            accepted = true;
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                D[i] = A[tri<P>(i, i)] == 0.0f ? 1.0f : A[tri<P>(i, i)];
+                s = f_fma(D[i] * x[i], x[i], s);
+            }
+            xnorm = f_sqrt(s);
+            delta = opt.factor * xnorm;
+            if (delta == 0.0f) delta = opt.factor;
+            fresh(opt);
+            return ier != 0;
+        }
+        ++nfev;
+        const float fn2 = 2.0f * chi;  // fnorm^2
+        const float actual = n.actual;
+        const bool bad = (n.flags & kFlagNonFinite) || !f_finite(actual);
+        const bool blown = bad || (fn2 - 2.0f * actual) >= 100.0f * fn2;  // 0.1 fnorm1 >= fnorm
+        const float rfn2 = f_rcp(fn2);
+        const float actred = blown ? -1.0f : 2.0f * actual * rfn2;
+        const float t1 = quad_form<P>(A, p) * rfn2;
+        const float t2 = par * pnorm * pnorm * rfn2;
+        const float prered = t1 + 2.0f * t2;
+        const float dirder = -(t1 + t2);
+        const float ratio = prered != 0.0f ? actred * f_rcp(prered) : 0.0f;
+        if (ratio <= 0.25f) {
+            float temp = actred >= 0.0f ? 0.5f : 0.5f * dirder * f_rcp(dirder + 0.5f * actred);
+            if (blown || temp < 0.1f) temp = 0.1f;
+            delta = temp * fminf(delta, pnorm * 10.0f);
+            par = par * f_rcp(temp);
+        } else if (par == 0.0f || ratio >= 0.75f) {
+            delta = 2.0f * pnorm;
+            par = 0.5f * par;
+        }
+        if (ratio >= 1e-4f) {  // successful iteration
+#pragma unroll
+            for (int i = 0; i < P; ++i) x[i] += p[i];
+            q0 = q1;
+            accepted = true;
+#pragma unroll
+            for (int i = 0; i < NTP; ++i) A[i] = n.A[i];
+#pragma unroll
+            for (int i = 0; i < P; ++i) g[i] = n.g[i];
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < P; ++i) s = f_fma(D[i] * x[i], x[i], s);
+            xnorm = f_sqrt(s);
+            chi -= actual;
+            first = false;
+        }
+        const bool fconv = fabsf(actred) <= opt.ftol && prered <= opt.ftol && 0.5f * ratio <= 1.0f;
+        if (fconv) ier = 1;
+        if (delta <= opt.xtol * xnorm) ier = fconv ? 3 : 2;
+        if (ier == 0 && nfev >= maxfev) ier = 5;
+        if (ier == 0 && !(delta > 0.0f)) ier = 7;
+        if (ier == 0 && accepted) fresh(opt);
+        return ier != 0;
+    }
+};
+
+// Per-fit state of the reference's lm() loop (lm.py:389-481).
+template <class Mo, bool MLE>
+struct StageB {
+    static constexpr int P = Mo::P;
+    static constexpr int NTP = NT<P>::value;
+    static constexpr bool kMle = MLE, kPred = true;
+    float x[P], A[NTP], g[P], dtd[P], xret[P];
+    typename Mo::Par q0;
+    float chisq_old, chisq_ret, lam;
+    int info, ev, n_acc, n_rej;
+    bool init, live;
+
+    DPH_HD void start(const float* p_ls) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) x[i] = xret[i] = p_ls[i];
+        Mo::prepare(x, q0);
+        chisq_old = chisq_ret = lam = 0.0f;
+        info = 5; ev = 0; n_acc = n_rej = 0;
+        init = true; live = false;
+    }
+    DPH_HD bool wants_chi() const { return init; }
+    DPH_HD bool propose(const Options& opt, float* p) {
+        live = false;
+#pragma unroll
+        for (int i = 0; i < P; ++i) p[i] = 0.0f;
+        if (init) return true;
+        if (opt.gtol > 0.0f) {  // lm.py:358-363, 409-411
+            float gm = 0.0f;
+#pragma unroll
+            for (int i = 0; i < P; ++i) gm = fmaxf(gm, fabsf(g[i]));
+            if (gm <= opt.gtol) { info = 4; return false; }
+        }
+        float U[NTP], d[P];
+        bool ok = chol_factor<P>(A, dtd, lam, U);
+        if (ok) {
+            chol_solve_neg<P>(U, g, d);
+#pragma unroll
+            for (int i = 0; i < P; ++i) ok = ok && f_finite(d[i]);
+        }
+        if (!ok) {
+            lam *= opt.factor;  // lm.py:426-428: the trip is consumed
+            return true;
+        }
+        float dn = 0.0f, xn2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) { dn = f_fma(d[i], d[i], dn); xn2 = f_fma(x[i], x[i], xn2); }
+        if (sqrtf(dn) <= opt.xtol * (sqrtf(xn2) + opt.xtol)) {  // lm.py:365-367, 430-432
+            info = 2;
+            return false;
+        }
+        live = true;
+#pragma unroll
+        for (int i = 0; i < P; ++i) p[i] = d[i];
+        return true;
+    }
+    DPH_HD bool consume(const Options& opt, const Normal<P>& n, const float* p, const typename Mo::Par& q1, bool& accepted) {
+        const int maxfev = opt.maxfev > 0 ? opt.maxfev : 100 * (P + 1);
+        accepted = false;
+        if (init) {
+            init = false;
+#pragma unroll
+            for (int i = 0; i < NTP; ++i) A[i] = n.A[i];
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                g[i] = n.g[i];
+                dtd[i] = A[tri<P>(i, i)];                     // lm.py:394
+                s = f_fma(dtd[i] * x[i], x[i], s);
+            }
+            chisq_old = chisq_ret = n.chi1;
+            lam = sqrtf(s);                                    // lm.py:398
+            if (!(lam > 0.0f) || !f_finite(lam)) lam = 100.0f;  // lm.py:399-400
+            accepted = true;
+            return false;
+        }
         if (live) {
 #pragma unroll
-            for (int i = 0; i < P; ++i) xret[i] = xn[i];
-            float actual = nrm.actual;
-            float predicted = (nrm.flags & 2) ? -kInf : nrm.predicted;  // chi2 = +inf when the predicted model dips below 0 (lm.py:62-64)
+            for (int i = 0; i < P; ++i) xret[i] = x[i] + p[i];
+            const float actual = n.actual;
+            // chi2 = +inf when the predicted model dips below 0 (lm.py:62-64)
+            const float predicted = (n.flags & kFlagPredNeg) ? -kInf : n.predicted;
             chisq_ret = chisq_old - actual;
             float rho = actual / predicted;
             if (actual < 0.0f || predicted < 0.0f || !f_finite(rho)) rho = 0.0f;  // lm.py:454-463
             if (rho > 1e-2f) {
                 if (actual <= opt.ftol * chisq_old) {  // lm.py:468-470
-                    info = 1; running = false;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < P; ++i) x[i] = xn[i];
-                    q0 = q1;
-                    px.cur = 1 - px.cur;
-                    chisq_old -= actual;
-#pragma unroll
-                    for (int i = 0; i < NTP; ++i) A[i] = nrm.A[i];
-#pragma unroll
-                    for (int i = 0; i < P; ++i) { g[i] = nrm.g[i]; dtd[i] = fmaxf(dtd[i], A[tri<P>(i, i)]); }  // lm.py:474
-                    lam = fmaxf(lam * 0.2f, 1e-7f);  // lm.py:475
-                    ++n_acc;
+                    info = 1;
+                    return true;
                 }
+#pragma unroll
+                for (int i = 0; i < P; ++i) x[i] = xret[i];
+                q0 = q1;
+                accepted = true;
+                chisq_old -= actual;
+#pragma unroll
+                for (int i = 0; i < NTP; ++i) A[i] = n.A[i];
+#pragma unroll
+                for (int i = 0; i < P; ++i) { g[i] = n.g[i]; dtd[i] = fmaxf(dtd[i], A[tri<P>(i, i)]); }  // lm.py:474
+                lam = fmaxf(lam * 0.2f, 1e-7f);  // lm.py:475
+                ++n_acc;
             } else {
                 lam = fminf(lam * 1.5f, 1e7f);  // lm.py:477
                 ++n_rej;
             }
         }
-        if (running) {
-            ++ev;
-            if (ev >= maxfev) { running = false; ev = maxfev - 1; }  // info stays 5 (lm.py:479-481)
+        ++ev;
+        if (ev >= maxfev) { ev = maxfev - 1; return true; }  // info stays 5 (lm.py:479-481)
+        return false;
+    }
+};
+
+// ------------------------------------------------------------------------------------- stage driver
+// Runs one stage for a stream of fits.  Every lane group owns one fit at a time and fetches the next one
+// from `io` as soon as its own has finished, so the groups of a warp never wait for each other's
+// iteration counts; the only warp-wide operations (the shuffles of the pass reductions) sit at
+// warp-uniform points of the loop.  `io` supplies fits (fetch) and takes results (store).
+template <class Stage, class Mo, int G, class IO>
+DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options& opt, IO& io) {
+    constexpr int P = Mo::P;
+    Stage st;
+    Normal<P> nrm;
+    float p[P];
+    typename Mo::Par q1;
+    typename Mo::Step step;
+    bool has = false, exhausted = false;
+    long long fit = -1;
+#pragma unroll
+    for (int i = 0; i < P; ++i) p[i] = 1.0f;
+    st.start(p);  // defined state for idle groups (values irrelevant)
+    for (;;) {
+        if (Lanes<G>::warp_any(!has && !exhausted)) {
+            if (!has && !exhausted) {
+                float pstart[P];
+                if (io.fetch(ln, px, pstart, fit)) {
+                    st.start(pstart);
+                    px.cur = 0;
+                    has = true;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!Lanes<G>::warp_any(has)) break;
+        bool pass = has;
+        if (has && !st.propose(opt, p)) {  // ended before the evaluation (xtest / gtest)
+            io.store(ln, st, fit);
+            has = false;
+            pass = false;
+        }
+        if (!pass) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) p[i] = 0.0f;
+        }
+        float xn[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) xn[i] = st.x[i] + p[i];
+        Mo::prepare(xn, q1);
+        Mo::prepare_step(st.q0, q1, p, step);
+        const bool init = st.init, want_chi = Lanes<G>::warp_any(pass && st.wants_chi());
+        trial_pass<Mo, Stage::kMle, Stage::kPred, true, G>(ln, px, st.q0, q1, step, init, want_chi, nrm);
+        if (Stage::kMle && Lanes<G>::warp_any(pass && (nrm.flags & kFlagIrregular))) {
+            Normal<P> slow;
+            trial_pass<Mo, Stage::kMle, Stage::kPred, false, G>(ln, px, st.q0, q1, step, init, want_chi, slow);
+            if (nrm.flags & kFlagIrregular) nrm = slow;
+        }
+        if (pass) {
+            bool accepted;
+            const bool done = st.consume(opt, nrm, p, q1, accepted);
+            if (accepted) px.cur = 1 - px.cur;
+            if (done) {
+                io.store(ln, st, fit);
+                has = false;
+            }
         }
     }
-#pragma unroll
-    for (int i = 0; i < P; ++i) out.x[i] = xret[i];
-    out.chisq = chisq_ret;
-    out.info = okA ? info : (ier == 0 ? -100 : -ier);
-    out.nfev = ev;
-    out.n_acc = n_acc;
-    out.n_rej = n_rej;
 }
 
 }  // namespace dphlm

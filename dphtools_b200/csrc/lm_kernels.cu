@@ -26,6 +26,9 @@ int get_ctx(int dev, DeviceCtx** out) {
     if (!c.counters) {
         CUDA_TRY(cudaMalloc(&c.counters, kCounterRing * sizeof(unsigned long long)));
         CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     *out = &c;
     return 0;
@@ -74,17 +77,27 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s) {
     a.opt = Options{d->ftol, d->xtol, d->gtol, d->factor, d->maxfev};
     const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w);
     const bool mle = d->method == DPHLM_MLE;
+    // workspace: pre-fit exit codes, and the pre-fit parameters when the caller does not want them
+    const size_t b_ier = ((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255);
+    const size_t b_pls = d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float);
+    char* ws = nullptr;
+    CUDA_TRY(cudaMallocAsync(&ws, b_ier + b_pls, s));
+    a.ier = reinterpret_cast<int*>(ws);
+    if (!d->p_ls) a.p_ls = reinterpret_cast<float*>(ws + b_ier);
+    int rc = -1;
     switch (d->model) {
-        case DPHLM_GAUSS2D: return launch_gauss2d(G, mle, a, ctx, s);
-        case DPHLM_GAUSS2D_ELLIPTICAL: return launch_gauss2d_elliptical(G, mle, a, ctx, s);
+        case DPHLM_GAUSS2D: rc = launch_gauss2d(G, mle, a, ctx, s); break;
+        case DPHLM_GAUSS2D_ELLIPTICAL: rc = launch_gauss2d_elliptical(G, mle, a, ctx, s); break;
         case DPHLM_MULTI_EXP:
             switch (d->n_param / 2) {
-                case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, ctx, s);
-                case 2: return launch_multi_exp2(d->n_param & 1, G, mle, a, ctx, s);
-                case 3: return launch_multi_exp3(d->n_param & 1, G, mle, a, ctx, s);
+                case 1: rc = launch_multi_exp1(d->n_param & 1, G, mle, a, ctx, s); break;
+                case 2: rc = launch_multi_exp2(d->n_param & 1, G, mle, a, ctx, s); break;
+                case 3: rc = launch_multi_exp3(d->n_param & 1, G, mle, a, ctx, s); break;
             }
+            break;
     }
-    return fail("unsupported model / n_param");
+    cudaFreeAsync(ws, s);
+    return rc;
 }
 
 size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }

@@ -42,8 +42,9 @@ struct KArgs {
     int* info;
     int* nfev;
     float* chisq;
-    float* p_ls;
-    int* counts;
+    float* p_ls;   // never null inside the kernels (user buffer or workspace)
+    int* ier;      // workspace [n_fits]: exit code of the pre-fit (100 = non-finite input data)
+    int* counts;   // optional
     unsigned long long* counter;
     long long n_fits;
     int h, w;
@@ -52,12 +53,107 @@ struct KArgs {
 
 constexpr int kWarps = DPH_WARPS;
 
+// per-fit stride of the shared-memory arrays: >= M and congruent to G modulo 32, so that the G-lane
+// groups of a warp touch disjoint banks
+__host__ __device__ inline int padded_stride(int M, int G) {
+    int s = M + ((G % 32) - (M % 32) + 32) % 32;
+    return s;
+}
+
+#if defined(__CUDACC__)
+// Fit supply / result sink of the pre-fit kernel.
+template <class Mo, int G>
+struct IoPrefit {
+    const KArgs& a;
+    __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, float* pstart, long long& fit) const {
+        constexpr int P = Mo::P;
+        const int src = __ffs(ln.gmask) - 1;
+        for (;;) {
+            unsigned long long idx = 0;
+            if (ln.lane == 0) idx = atomicAdd(a.counter, 1ull);
+            idx = __shfl_sync(ln.gmask, idx, src);
+            if ((long long)idx >= a.n_fits) return false;
+            const float* d = a.data + idx * px.M;
+            bool bad = false;
+            for (int i = ln.lane; i < px.M; i += G) {
+                float v = __ldg(d + i);
+                bad |= !f_finite(v);
+                px.y[i] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < P; ++k) pstart[k] = __ldg(a.p0 + idx * P + k);
+            bad = __any_sync(ln.gmask, bad);
+            __syncwarp(ln.gmask);
+            if (!bad) { fit = (long long)idx; return true; }
+            if (ln.lane == 0) {  // the reference raises ValueError (lm.py:651-652)
+                a.ier[idx] = 100;
+#pragma unroll
+                for (int k = 0; k < P; ++k) a.p_ls[idx * P + k] = pstart[k];
+                if (a.counts) reinterpret_cast<int4*>(a.counts)[idx] = make_int4(0, 0, 0, 0);
+            }
+        }
+    }
+    __device__ void store(const Lanes<G>& ln, const StageA<Mo>& st, long long fit) const {
+        if (ln.lane != 0) return;
+#pragma unroll
+        for (int k = 0; k < Mo::P; ++k) a.p_ls[fit * Mo::P + k] = st.x[k];
+        a.ier[fit] = st.ier;
+        if (a.counts) a.counts[4 * fit] = st.nfev;
+    }
+};
+
+// Fit supply / result sink of the main (lm) kernel: starts from the pre-fit results.
 template <class Mo, bool MLE, int G>
-__global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_fit_kernel(const KArgs a) {
+struct IoMain {
+    const KArgs& a;
+    __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, float* pstart, long long& fit) const {
+        constexpr int P = Mo::P;
+        const int src = __ffs(ln.gmask) - 1;
+        for (;;) {
+            unsigned long long idx = 0;
+            if (ln.lane == 0) idx = atomicAdd(a.counter, 1ull);
+            idx = __shfl_sync(ln.gmask, idx, src);
+            if ((long long)idx >= a.n_fits) return false;
+            const int ier = __ldg(a.ier + idx);
+#pragma unroll
+            for (int k = 0; k < P; ++k) pstart[k] = a.p_ls[idx * P + k];
+            if (ier >= 1 && ier <= 4) {
+                const float* d = a.data + idx * px.M;
+                for (int i = ln.lane; i < px.M; i += G) {
+                    float v = __ldg(d + i);
+                    px.y[i] = MLE ? clamp_nonneg(v) : v;  // lm.py:127
+                }
+                __syncwarp(ln.gmask);
+                fit = (long long)idx;
+                return true;
+            }
+            if (ln.lane == 0) {  // the pre-fit failed: report it, do not fit (scipy raises, lm.py:642-644)
+#pragma unroll
+                for (int k = 0; k < P; ++k) a.popt[idx * P + k] = pstart[k];
+                a.info[idx] = ier == 0 ? -99 : -ier;
+                a.nfev[idx] = 0;
+                a.chisq[idx] = 0.0f;
+                if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
+            }
+        }
+    }
+    __device__ void store(const Lanes<G>& ln, const StageB<Mo, MLE>& st, long long fit) const {
+        if (ln.lane != 0) return;
+#pragma unroll
+        for (int k = 0; k < Mo::P; ++k) a.popt[fit * Mo::P + k] = st.xret[k];
+        a.info[fit] = st.info;
+        a.nfev[fit] = st.ev;
+        a.chisq[fit] = st.chisq_ret;
+        if (a.counts) { a.counts[4 * fit + 1] = st.n_acc; a.counts[4 * fit + 2] = st.n_rej; a.counts[4 * fit + 3] = 0; }
+    }
+};
+
+template <class Stage, class Mo, int G, class IO>
+__global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(const KArgs a) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int FPW = 32 / G;  // fits per warp
-    constexpr int P = Mo::P;
+    constexpr int FPW = 32 / G;  // fits in flight per warp
     const int M = a.h * a.w;
+    const int stride = padded_stride(M, G);
     Coord* cxy = reinterpret_cast<Coord*>(smem);
     for (int i = threadIdx.x; i < M; i += blockDim.x) {
         Coord c;
@@ -66,62 +162,16 @@ __global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_fit_kernel(const 
         cxy[i] = c;
     }
     __syncthreads();
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G;
-    float* wy = smem + 2 * M + warp * (FPW * M * (1 + 2 * Mo::NE));
-    float* we = wy + FPW * M;
-    Lanes<G> ln{lane % G};
-
-    for (;;) {
-        unsigned long long batch = 0;
-        if (lane == 0) batch = atomicAdd(a.counter, 1ull);
-        batch = __shfl_sync(0xffffffffu, batch, 0);
-        const long long f0 = (long long)batch * FPW;
-        if (f0 >= a.n_fits) break;
-        const long long left = a.n_fits - f0;
-        const int nload = int(left < FPW ? left : FPW) * M;
-        const float* src = a.data + f0 * M;
-        unsigned badmask = 0;
-        for (int i = lane; i < FPW * M; i += 32) {
-            float v = i < nload ? __ldg(src + i) : 0.0f;
-            if (!f_finite(v)) badmask |= 1u << (i / M);
-            wy[i] = MLE ? clamp_nonneg(v) : v;
-        }
-        badmask = __reduce_or_sync(0xffffffffu, badmask);
-        __syncwarp();
-
-        const long long fit = f0 + grp;
-        const bool active = fit < a.n_fits;
-        const bool bad = (badmask >> grp) & 1u;
-        float p0[P];
-#pragma unroll
-        for (int k = 0; k < P; ++k) p0[k] = active ? __ldg(a.p0 + fit * P + k) : 1.0f;
-        PixelState<Mo::NE> px{wy + grp * M, we + grp * (2 * Mo::NE * M), cxy, M, 0};
-        FitResult<P> r;
-        fit_one<Mo, MLE, G>(ln, px, p0, a.opt, active && !bad, r);
-        if (active && ln.lane == 0) {
-            if (bad) {
-                r.info = -100;
-#pragma unroll
-                for (int k = 0; k < P; ++k) r.x[k] = r.p_ls[k] = p0[k];
-            }
-#pragma unroll
-            for (int k = 0; k < P; ++k) a.popt[fit * P + k] = r.x[k];
-            a.info[fit] = r.info;
-            a.nfev[fit] = r.nfev;
-            a.chisq[fit] = r.chisq;
-            if (a.p_ls) {
-#pragma unroll
-                for (int k = 0; k < P; ++k) a.p_ls[fit * P + k] = r.p_ls[k];
-            }
-            if (a.counts) {
-                reinterpret_cast<int4*>(a.counts)[fit] = make_int4(r.nfev_ls, r.n_acc, r.n_rej, 0);
-            }
-        }
-        __syncwarp();
-    }
+    const int region = stride * (1 + 2 * Mo::NE);
+    float* base = smem + 2 * ((M + 1) & ~1) + (warp * FPW + grp) * region;
+    Lanes<G> ln{lane % G, G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G))};
+    PixelState<Mo::NE> px{base, base + stride, cxy, M, stride, 0};
+    IO io{a};
+    run_stage<Stage, Mo, G>(ln, px, a.opt, io);
 }
+#endif
 
 struct DeviceCtx {
     std::mutex mu;
@@ -137,19 +187,15 @@ struct DeviceCtx {
 };
 constexpr int kCounterRing = 1024;
 
-template <class Mo, bool MLE, int G>
-int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
+template <class Kern>
+int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream) {
     KArgs a = a0;
-    const int M = a.h * a.w;
-    constexpr int FPW = 32 / G;
-    const size_t smem = sizeof(float) * (2 * (size_t)M + (size_t)kWarps * FPW * M * (1 + 2 * Mo::NE));
-    auto kern = dphlm_fit_kernel<Mo, MLE, G>;
-    if (smem > 227 * 1024) return fail("ROI too large for the shared-memory layout of this group size");
+    if (smem > 227 * 1024) return ::dphlm::fail("ROI too large for the shared-memory layout of this group size");
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem));
-    if (occ < 1) return fail("kernel does not fit on an SM");
+    if (occ < 1) return ::dphlm::fail("kernel does not fit on an SM");
     unsigned slot;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -157,9 +203,8 @@ int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
     }
     a.counter = ctx->counters + slot;
     CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
-    const long long batches = (a.n_fits + FPW - 1) / FPW;
     long long grid = (long long)ctx->sms * occ;
-    const long long need = (batches + kWarps - 1) / kWarps;
+    const long long need = (a.n_fits + (long long)kWarps * fpw - 1) / ((long long)kWarps * fpw);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
@@ -167,6 +212,16 @@ int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
     return 0;
 }
 
+// both stages of curve_fit(method='ls'|'mle') for one batch: pre-fit kernel, then the lm() kernel
+template <class Mo, bool MLE, int G>
+int launch(const KArgs& a, DeviceCtx* ctx, cudaStream_t stream) {
+    const int M = a.h * a.w;
+    constexpr int FPW = 32 / G;
+    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * padded_stride(M, G) * (1 + 2 * Mo::NE));
+    int rc = launch_stage(dphlm_stage_kernel<StageA<Mo>, Mo, G, IoPrefit<Mo, G>>, a, FPW, smem, ctx, stream);
+    if (rc) return rc;
+    return launch_stage(dphlm_stage_kernel<StageB<Mo, MLE>, Mo, G, IoMain<Mo, MLE, G>>, a, FPW, smem, ctx, stream);
+}
 
 // one per model family, defined in lm_inst_*.cu
 int launch_gauss2d(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);

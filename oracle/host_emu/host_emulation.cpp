@@ -9,9 +9,70 @@
 
 using namespace dphlm;
 
+struct Buffers {
+    int M;
+    long n;
+    const float* data;
+    const float* p0;
+    float *popt, *p_ls, *chisq;
+    int *info, *nfev, *counts;
+    std::vector<int> ier;
+};
+
+template <class Mo>
+struct HostIoPrefit {
+    Buffers& b;
+    long next = 0;
+    bool fetch(const Lanes<1>&, PixelState<Mo::NE>& px, float* pstart, long long& fit) {
+        for (;;) {
+            if (next >= b.n) return false;
+            long idx = next++;
+            bool bad = false;
+            for (int i = 0; i < b.M; ++i) { float v = b.data[idx * b.M + i]; bad |= !std::isfinite(v); px.y[i] = v; }
+            for (int k = 0; k < Mo::P; ++k) pstart[k] = b.p0[idx * Mo::P + k];
+            if (!bad) { fit = idx; return true; }
+            b.ier[idx] = 100;
+            for (int k = 0; k < Mo::P; ++k) b.p_ls[idx * Mo::P + k] = pstart[k];
+            for (int k = 0; k < 4; ++k) b.counts[4 * idx + k] = 0;
+        }
+    }
+    void store(const Lanes<1>&, const StageA<Mo>& st, long long fit) {
+        for (int k = 0; k < Mo::P; ++k) b.p_ls[fit * Mo::P + k] = st.x[k];
+        b.ier[fit] = st.ier;
+        b.counts[4 * fit] = st.nfev;
+    }
+};
+
 template <class Mo, bool MLE>
-static void run(int h, int w, long n, const float* data, const float* xaxis, const float* p0, const Options& opt,
-                float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts) {
+struct HostIoMain {
+    Buffers& b;
+    long next = 0;
+    bool fetch(const Lanes<1>&, PixelState<Mo::NE>& px, float* pstart, long long& fit) {
+        for (;;) {
+            if (next >= b.n) return false;
+            long idx = next++;
+            int ier = b.ier[idx];
+            for (int k = 0; k < Mo::P; ++k) pstart[k] = b.p_ls[idx * Mo::P + k];
+            if (ier >= 1 && ier <= 4) {
+                for (int i = 0; i < b.M; ++i) { float v = b.data[idx * b.M + i]; px.y[i] = MLE ? clamp_nonneg(v) : v; }
+                fit = idx;
+                return true;
+            }
+            for (int k = 0; k < Mo::P; ++k) b.popt[idx * Mo::P + k] = pstart[k];
+            b.info[idx] = ier == 0 ? -99 : -ier;
+            b.nfev[idx] = 0;
+            b.chisq[idx] = 0.f;
+        }
+    }
+    void store(const Lanes<1>&, const StageB<Mo, MLE>& st, long long fit) {
+        for (int k = 0; k < Mo::P; ++k) b.popt[fit * Mo::P + k] = st.xret[k];
+        b.info[fit] = st.info; b.nfev[fit] = st.ev; b.chisq[fit] = st.chisq_ret;
+        b.counts[4 * fit + 1] = st.n_acc; b.counts[4 * fit + 2] = st.n_rej; b.counts[4 * fit + 3] = 0;
+    }
+};
+
+template <class Mo, bool MLE>
+static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b) {
     const int M = h * w;
     std::vector<Coord> cxy(M);
     for (int i = 0; i < M; ++i) {
@@ -19,30 +80,24 @@ static void run(int h, int w, long n, const float* data, const float* xaxis, con
         else { cxy[i].x = float(i % w); cxy[i].y = float(i / w); }
     }
     std::vector<float> y(M), e(2 * Mo::NE * M);
-    Lanes<1> ln{0};
-    for (long f = 0; f < n; ++f) {
-        for (int i = 0; i < M; ++i) {
-            float v = data[f * M + i];
-            y[i] = MLE ? clamp_nonneg(v) : v;
-        }
-        PixelState<Mo::NE> px{y.data(), e.data(), cxy.data(), M, 0};
-        FitResult<Mo::P> r;
-        fit_one<Mo, MLE, 1>(ln, px, p0 + f * Mo::P, opt, true, r);
-        for (int k = 0; k < Mo::P; ++k) { popt[f * Mo::P + k] = r.x[k]; p_ls[f * Mo::P + k] = r.p_ls[k]; }
-        info[f] = r.info; nfev[f] = r.nfev; chisq[f] = r.chisq;
-        counts[4 * f + 0] = r.nfev_ls; counts[4 * f + 1] = r.n_acc; counts[4 * f + 2] = r.n_rej; counts[4 * f + 3] = 0;
-    }
+    Lanes<1> ln{0, 1u};
+    PixelState<Mo::NE> px{y.data(), e.data(), cxy.data(), M, M, 0};
+    HostIoPrefit<Mo> ioa{b};
+    run_stage<StageA<Mo>, Mo, 1>(ln, px, opt, ioa);
+    HostIoMain<Mo, MLE> iob{b};
+    run_stage<StageB<Mo, MLE>, Mo, 1>(ln, px, opt, iob);
 }
 
 extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, long n, const float* data,
                              const float* xaxis, const float* p0, float ftol, float xtol, float gtol, float factor,
                              int maxfev, float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts) {
     Options opt{ftol, xtol, gtol, factor, maxfev};
-#define RUN(...)                                                                                                 \
-    do {                                                                                                         \
-        if (method) run<__VA_ARGS__, true>(h, w, n, data, xaxis, p0, opt, popt, p_ls, info, nfev, chisq, counts);          \
-        else run<__VA_ARGS__, false>(h, w, n, data, xaxis, p0, opt, popt, p_ls, info, nfev, chisq, counts);                \
-        return 0;                                                                                                \
+    Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0)};
+#define RUN(...)                                                 \
+    do {                                                         \
+        if (method) run<__VA_ARGS__, true>(h, w, xaxis, opt, b);  \
+        else run<__VA_ARGS__, false>(h, w, xaxis, opt, b);        \
+        return 0;                                                \
     } while (0)
     if (model == 0 && n_param == 5) RUN(Gauss2D);
     if (model == 1 && n_param == 7) RUN(Gauss2DElliptical);
