@@ -58,31 +58,30 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kInf = __builtin_huge_valf();
 
-// log1p(u), relative accuracy ~1e-7 for |u| <= 1/8 (Taylor, degree 8), lg2-based beyond.
+// log1p(u): Taylor series of degree 6 for |u| <= 1/32 (truncation < 2e-10 relative), lg2-based beyond
+// (absolute error ~2e-7 there, on steps that change the model by more than 3%).
+constexpr float kLog1pSmall = 0.03125f;
 DPH_HD float log1p_acc(float u) {
-    float p = -0.125f;
-    p = f_fma(p, u, 1.0f / 7.0f);
-    p = f_fma(p, u, -1.0f / 6.0f);
+    float p = -1.0f / 6.0f;
     p = f_fma(p, u, 0.2f);
     p = f_fma(p, u, -0.25f);
     p = f_fma(p, u, 1.0f / 3.0f);
     p = f_fma(p, u, -0.5f);
     p = f_fma(p * u, u, u);
     float big = kLn2 * f_lg2(fmaxf(1.0f + u, 1e-37f));
-    return fabsf(u) <= 0.125f ? p : big;
+    return fabsf(u) <= kLog1pSmall ? p : big;
 }
 
-// expm1(a) for |a| <= 1/8 (Taylor, degree 7); callers handle larger |a| by direct differences.
+// expm1(a) for |a| <= 1/16 (Taylor, degree 5, truncation < 2e-9 relative); callers handle larger |a| by
+// direct differences of the stored exponentials.
 DPH_HD float expm1_small(float a) {
-    float p = 1.0f / 5040.0f;
-    p = f_fma(p, a, 1.0f / 720.0f);
-    p = f_fma(p, a, 1.0f / 120.0f);
+    float p = 1.0f / 120.0f;
     p = f_fma(p, a, 1.0f / 24.0f);
     p = f_fma(p, a, 1.0f / 6.0f);
     p = f_fma(p, a, 0.5f);
     return f_fma(p * a, a, a);
 }
-constexpr float kSmallArg = 0.125f;
+constexpr float kSmallArg = 0.0625f;
 
 // ------------------------------------------------------------------------------- small dense algebra
 // packed upper triangle, row-major: (i,j), i <= j
@@ -167,8 +166,9 @@ DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
 struct Gauss2D {  // amp, x0, y0, sigma, offset
     static constexpr int P = 5, NE = 1;
     struct Par { float amp, x0, y0, sig, off, s2, s3, nh; };
-    struct Step { float d0, d1, d2, d3, d4, h1, ds, c2, c3; };
+    struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
     struct Geo { float dx, dy, r2; };
+    struct Diff { float dot, dr2, r20; };
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
         float is = f_rcp(q.sig);
@@ -186,21 +186,27 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
         J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = q.amp * e[0] * q.s3 * g.r2; J[4] = 1.0f;
     }
     DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
-        s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3]; s.d4 = d[4];
-        s.h1 = 0.5f * b.s2;                                              // 1/(2 sigma_new^2)
-        s.ds = -d[3] * (2.0f * a.sig + d[3]) * 0.5f * a.s2 * b.s2;       // 1/(2 s_n^2) - 1/(2 s_o^2)
+        s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d4 = d[4];
+        s.nh1 = -0.5f * b.s2;                                             // -1/(2 sigma_new^2)
+        s.nds = d[3] * (2.0f * a.sig + d[3]) * 0.5f * a.s2 * b.s2;        // -(1/(2 s_n^2) - 1/(2 s_o^2))
+        s.ndd = -f_fma(d[1], d[1], d[2] * d[2]);
         s.c2 = a.amp * a.s2; s.c3 = a.amp * a.s3 * d[3];
+        s.k0 = f_fma(-s.c2, s.ndd, d[0]);                                 // d0 + c2 (d1^2 + d2^2)
     }
-    // ga/ea: geometry and exponentials at the OLD point, eb at the new one
-    DPH_HD static float delta(const Par& a, const Step& s, const Geo& ga, const float* ea, const float* eb) {
-        float dr2 = -s.d1 * (2.0f * ga.dx - s.d1) - s.d2 * (2.0f * ga.dy - s.d2);
-        float darg = -f_fma(dr2, s.h1, ga.r2 * s.ds);
+    // per-pixel step quantities, from the geometry at the NEW point (dx_old = dx_new + d1, ...)
+    DPH_HD static void diff(const Par&, const Step& s, const Geo& g1, Diff& df) {
+        df.dot = f_fma(g1.dx, s.d1, g1.dy * s.d2);
+        df.dr2 = f_fma(-2.0f, df.dot, s.ndd);       // r2_new - r2_old
+        df.r20 = g1.r2 - df.dr2;                    // r2_old
+    }
+    DPH_HD static float delta(const Par& a, const Step& s, const Diff& df, const float* ea, const float* eb) {
+        float darg = f_fma(df.dr2, s.nh1, df.r20 * s.nds);
         float de = fabsf(darg) <= kSmallArg ? ea[0] * expm1_small(darg) : eb[0] - ea[0];
         return f_fma(s.d0, eb[0], f_fma(a.amp, de, s.d4));
     }
-    DPH_HD static float jdx(const Par& a, const Step& s, const Geo& ga, const float* ea) {
-        float lin = f_fma(s.c2, f_fma(ga.dx, s.d1, ga.dy * s.d2), s.c3 * ga.r2);
-        return f_fma(ea[0], s.d0 + lin, s.d4);
+    DPH_HD static float jdx(const Par&, const Step& s, const Diff& df, const float* ea) {
+        float lin = f_fma(s.c2, df.dot, f_fma(s.c3, df.r20, s.k0));
+        return f_fma(ea[0], lin, s.d4);
     }
 };
 
@@ -209,6 +215,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy; };
     struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day; };
     struct Geo { float dx, dy, u, v; };
+    struct Diff { float dx, dy, u, v; };
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];
 #if defined(__CUDA_ARCH__)
@@ -257,7 +264,12 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         s.dax = -d[3] * (2.0f * a.sx + d[3]) * a.ax * b.ax;
         s.day = -d[4] * (2.0f * a.sy + d[4]) * a.ay * b.ay;
     }
-    DPH_HD static float delta(const Par& a, const Step& s, const Geo& ga, const float* ea, const float* eb) {
+    DPH_HD static void diff(const Par& a, const Step& s, const Geo& g1, Diff& df) {
+        df.dx = g1.dx + s.d1; df.dy = g1.dy + s.d2;  // offsets from the OLD centre
+        df.u = f_fma(a.c, df.dx, a.s * df.dy);
+        df.v = f_fma(a.c, df.dy, -a.s * df.dx);
+    }
+    DPH_HD static float delta(const Par& a, const Step& s, const Diff& ga, const float* ea, const float* eb) {
         float du = f_fma(s.dc, ga.dx, s.dsn * ga.dy) - f_fma(s.cb, s.d1, s.sb * s.d2);
         float dv = f_fma(s.dc, ga.dy, -s.dsn * ga.dx) - f_fma(s.cb, s.d2, -s.sb * s.d1);
         float du2 = du * f_fma(2.0f, ga.u, du);
@@ -267,12 +279,16 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         float de = fabsf(darg) <= kSmallArg ? ea[0] * expm1_small(darg) : eb[0] - ea[0];
         return f_fma(s.d0, eb[0], f_fma(a.amp, de, s.d6));
     }
-    DPH_HD static float jdx(const Par& a, const Step& s, const Geo& ga, const float* ea) {
-        float J[P];
-        jac(a, ga, ea, J);
+    DPH_HD static float jdx(const Par& a, const Step& s, const Diff& ga, const float* ea) {
+        float ae = a.amp * ea[0];
+        float uax = ga.u * a.ax, vay = ga.v * a.ay;
         float r = s.d6;
-        r = f_fma(J[0], s.d0, r); r = f_fma(J[1], s.d1, r); r = f_fma(J[2], s.d2, r);
-        r = f_fma(J[3], s.d3, r); r = f_fma(J[4], s.d4, r); r = f_fma(J[5], s.d5, r);
+        r = f_fma(ea[0], s.d0, r);
+        r = f_fma(ae * f_fma(uax, a.c, -vay * a.s), s.d1, r);
+        r = f_fma(ae * f_fma(uax, a.s, vay * a.c), s.d2, r);
+        r = f_fma(ae * ga.u * uax * a.isx, s.d3, r);
+        r = f_fma(ae * ga.v * vay * a.isy, s.d4, r);
+        r = f_fma(ae * ga.u * ga.v * (a.ay - a.ax), s.d5, r);
         return r;
     }
 };
@@ -284,6 +300,7 @@ struct MultiExp {
     struct Par { float a[NEXP], k[NEXP], off; };
     struct Step { float da[NEXP], dk[NEXP], doff; };
     struct Geo { float x; };
+    struct Diff { float x; };
     DPH_HD static void prepare(const float* p, Par& q) {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) { q.a[i] = p[2 * i]; q.k[i] = p[2 * i + 1]; }
@@ -310,7 +327,8 @@ struct MultiExp {
         for (int i = 0; i < NEXP; ++i) { s.da[i] = d[2 * i]; s.dk[i] = d[2 * i + 1]; }
         s.doff = OFFSET ? d[2 * NEXP] : 0.0f;
     }
-    DPH_HD static float delta(const Par& a, const Step& s, const Geo& ga, const float* ea, const float* eb) {
+    DPH_HD static void diff(const Par&, const Step&, const Geo& g1, Diff& df) { df.x = g1.x; }
+    DPH_HD static float delta(const Par& a, const Step& s, const Diff& ga, const float* ea, const float* eb) {
         float r = s.doff;
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) {
@@ -320,7 +338,7 @@ struct MultiExp {
         }
         return r;
     }
-    DPH_HD static float jdx(const Par& a, const Step& s, const Geo& ga, const float* ea) {
+    DPH_HD static float jdx(const Par& a, const Step& s, const Diff& ga, const float* ea) {
         float r = s.doff;
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) r = f_fma(ea[i], f_fma(-a.a[i] * ga.x, s.dk[i], s.da[i]), r);
@@ -446,46 +464,48 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
                        Normal<Mo::P>& n) {
     constexpr int P = Mo::P, NE = Mo::NE;
     n.clear();
-    const float* e0p[NE];
-    float* e1p[NE];
-#pragma unroll
-    for (int j = 0; j < NE; ++j) { e0p[j] = px.ebuf(px.cur, j); e1p[j] = px.ebuf(1 - px.cur, j); }
-    const float* ys = px.y;
-    const Coord* cxy = px.cxy;
+    // running pointers (one element per lane and trip)
+    const float* e0p = px.ebuf(px.cur, 0) + ln.lane;
+    float* e1p = px.ebuf(1 - px.cur, 0) + ln.lane;
+    const float* yp = px.y + ln.lane;
+    const Coord* cp = px.cxy + ln.lane;
+    const int stride = px.stride;
+    float lo = 1.0f;  // smallest model value met (regular case: stays > 0)
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
 #endif
-    for (int i = ln.lane; i < px.M; i += G) {
-        typename Mo::Geo g0, g1;
+    for (int i = ln.lane; i < px.M; i += G, e0p += G, e1p += G, yp += G, cp += G) {
+        typename Mo::Geo g1;
+        typename Mo::Diff df;
         float e0[NE], e1[NE], J[P];
-        const Coord c = cxy[i];
-        Mo::geometry(q0, c.x, c.y, g0);
+        const Coord c = *cp;
         Mo::geometry(q1, c.x, c.y, g1);
         Mo::expo(q1, g1, e1);
 #pragma unroll
         for (int j = 0; j < NE; ++j) {
-            float t = e0p[j][i];
+            float t = e0p[j * stride];
             e0[j] = init ? e1[j] : t;
-            e1p[j][i] = e1[j];
+            e1p[j * stride] = e1[j];
         }
-        const float y = ys[i];
+        const float y = *yp;
+        Mo::diff(q0, st, g1, df);
         const float f0 = Mo::value(q0, e0);
         const float f1 = Mo::value(q1, e1);
-        const float dl = Mo::delta(q0, st, g0, e0, e1);
+        const float dl = Mo::delta(q0, st, df, e0, e1);
         Mo::jac(q1, g1, e1, J);
         if (MLE) {
             if (FAST) {
                 const float f0c = fmaxf(f0, 0.0f), f1c = fmaxf(f1, 0.0f);
                 const float rf0 = f_rcp(f0c);
                 n.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
-                float lo = fminf(f0c, f1c);
                 if (PRED) {
-                    const float jd = Mo::jdx(q0, st, g0, e0);
+                    const float jd = Mo::jdx(q0, st, df, e0);
                     const float dp = dl + jd;
-                    lo = fminf(lo, f1c + jd);
+                    lo = fminf(lo, fminf(f0c, fminf(f1c, f1c + jd)));
                     n.predicted += f_fma(y, log1p_acc(dp * rf0), -dp);
+                } else {
+                    lo = fminf(lo, fminf(f0c, f1c));
                 }
-                if (!(lo > 0.0f)) n.flags |= kFlagIrregular;
                 const float rf1 = f_rcp(f1c);
                 const float yf = y * rf1;
                 accumulate<P>(n, J, yf * rf1, 1.0f - yf);
@@ -498,7 +518,7 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
                 if (reg) n.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
                 else n.actual += mle_term_direct(f0c, y) - mle_term_direct(f1c, y);
                 if (PRED) {
-                    const float jd = Mo::jdx(q0, st, g0, e0);
+                    const float jd = Mo::jdx(q0, st, df, e0);
                     const float fp = f1c + jd;
                     if (fp < 0.0f) n.flags |= kFlagPredNeg;
                     if (reg && fp > 0.0f) {
@@ -517,13 +537,14 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
             const float r0 = f0 - y, r1 = f1 - y;
             n.actual = f_fma(-dl, f_fma(0.5f, dl, r0), n.actual);
             if (PRED) {
-                const float dp = dl + Mo::jdx(q0, st, g0, e0);
+                const float dp = dl + Mo::jdx(q0, st, df, e0);
                 n.predicted = f_fma(-dp, f_fma(0.5f, dp, r0), n.predicted);
             }
             n.chi1 = f_fma(0.5f * r1, r1, n.chi1);
             accumulate<P>(n, J, 1.0f, r1);
         }
     }
+    if (MLE && FAST && !(lo > 0.0f)) n.flags |= kFlagIrregular;  // also catches NaN
     n.reduce(ln);
     if (!MLE && !f_finite(n.chi1)) n.flags |= kFlagNonFinite;
 }
