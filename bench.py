@@ -192,48 +192,42 @@ def main():
     ms_total = float(ms.item())
     value = world * n * args.steps / (ms_total * 1e-3)
 
-    # ---- the dominant (only) kernel alone: per-launch duration and algorithmic flops from its own counters
-    kt = []
-    flops = []
+    # ---- the two kernels alone: per-launch durations (CUDA events recorded by the library on the launch
+    # stream around each kernel) and algorithmic flops from the per-fit counters the kernels return
+    t_pre, t_main, fl_pre, fl_main = [], [], [], []
     for i in range(min(args.steps, 8)):
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = step(i, counts=True)
-        b.record()
-        torch.cuda.synchronize()
-        kt.append(a.elapsed_time(b) * 1e-3)
+        r = dph.curve_fit_batch(models.gauss2d, d_data[i % N_SETS], d_p0[i % N_SETS], "mle", return_counts=True,
+                                group_lanes=args.group_lanes, timing=True)
+        ms_pre, ms_main = _lib.last_kernel_ms()
+        t_pre.append(ms_pre * 1e-3)
+        t_main.append(ms_main * 1e-3)
         c = r.counts.sum(0).double().cpu().numpy()
-        flops.append(ROI * ROI * (F_0 * n + F_ACC * c[1] + F_REJ * c[2] + F_LS * c[0]))
-    k_s = float(np.mean(kt))
-    achieved_tf = float(np.mean(flops)) / k_s / 1e12
+        fl_pre.append(ROI * ROI * F_LS * c[0])
+        fl_main.append(ROI * ROI * (F_0 * n + F_ACC * c[1] + F_REJ * c[2]))
+    k_pre, k_main = float(np.mean(t_pre)), float(np.mean(t_main))
+    k_s = k_pre + k_main
+    flops = [a + b for a, b in zip(fl_pre, fl_main)]
+    achieved_tf = float(np.mean(fl_main)) / k_main / 1e12      # dominant kernel: the lm() loop
+    step_tf = float(np.mean(flops)) / k_s / 1e12               # both kernels of a step
     props = torch.cuda.get_device_properties(dev)
 
     # ---- end to end through the public API with pinned host buffers (H2D + fit + D2H per step)
-    lib = _lib.lib()
-    import ctypes
-
-    def pinned(shape, dtype):
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        ptr = lib.dphlm_host_alloc(nbytes)
-        assert ptr, "pinned allocation failed"
-        buf = (ctypes.c_char * nbytes).from_address(ptr)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape), ptr
-
     h_sets = []
     for s in sets[:2]:
-        hd, p1 = pinned(s["data"].shape, np.float32)
-        hp, p2 = pinned(s["p0"].shape, np.float32)
+        hd, hp = dph.pinned_empty(s["data"].shape), dph.pinned_empty(s["p0"].shape)
         hd[...] = s["data"]
         hp[...] = s["p0"]
-        h_sets.append((hd, hp, p1, p2))
+        h_sets.append((hd, hp))
+    h_out = dph.BatchResult(dph.pinned_empty((n, 5)), dph.pinned_empty(n, np.int32), dph.pinned_empty(n, np.int32),
+                            dph.pinned_empty(n), None, None)
     e2e_steps = max(3, min(args.steps, 10))
     for i in range(2):
-        dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local)
+        dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local, out=h_out)
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        r_host = dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local)
+        r_host = dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local, out=h_out)
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -263,13 +257,18 @@ def main():
                 "converged_fraction": float(((info >= 1) & (info <= 4)).mean()),
             },
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": n * (ROI * ROI + 5) * 4,
-                    "d2h_bytes_per_step": n * (5 + 3) * 4, "steps": e2e_steps, "host_memory": "pinned (dphlm_host_alloc)"},
-            "gpu_launches": args.steps,
+                    "d2h_bytes_per_step": n * (5 + 3) * 4, "steps": e2e_steps, "host_memory": "pinned inputs and outputs (dphtools_b200.pinned_empty)",
+                    "converged_fraction": float(((r_host.info >= 1) & (r_host.info <= 4)).mean())},
+            "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
-                "traffic": None, "kernel": "dphlm_fit_kernel<Gauss2D,MLE>", "kernel_ms": k_s * 1e3,
+                "traffic": None, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481)",
+                "kernel_ms": k_main * 1e3, "share_of_step": k_main / k_s,
                 "peak_source": "SMs x 128 lanes x 2 x max SM clock (no fp32 entry in MEASURED_PEAKS.json)",
-                "flops_per_fit": float(np.mean(flops)) / n,
+                "flops_per_fit": float(np.mean(fl_main)) / n,
+                "prefit_kernel": {"kernel": "dphlm_stage_kernel<StageA<Gauss2D>> (MINPACK pre-fit, lm.py:642-648)", "kernel_ms": k_pre * 1e3,
+                                  "achieved": float(np.mean(fl_pre)) / k_pre / 1e12, "flops_per_fit": float(np.mean(fl_pre)) / n},
+                "step": {"achieved": step_tf, "frac": step_tf / fp32_peak_tf, "flops_per_fit": float(np.mean(flops)) / n},
                 "hbm": {"achieved": BYTES_PER_FIT * n / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": BYTES_PER_FIT * n / k_s / 1e9 / hbm_peak, "bytes_per_fit": BYTES_PER_FIT,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"},
@@ -290,8 +289,6 @@ def main():
                                    "sample": "first %d ROIs of input set 0, float64 oracle port of curve_fit(method='mle'), one process per core" % n_cpu,
                                    "parity_on_sample": rep}
         print(json.dumps(out))
-    for hd, hp, p1, p2 in h_sets:
-        del hd, hp
     if world > 1:
         dist.destroy_process_group()
 

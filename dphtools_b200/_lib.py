@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("DPHLM_LIB") or os.path.join(os.path.dirname(os.path.a
 
 SYMBOLS = [
     "dphlm_desc_init", "dphlm_fit_batch", "dphlm_fit_batch_host", "dphlm_host_alloc", "dphlm_host_free",
-    "dphlm_device_count", "dphlm_version", "dphlm_last_error",
+    "dphlm_device_count", "dphlm_version", "dphlm_last_error", "dphlm_last_kernel_ms",
 ]
 
 
@@ -53,10 +53,23 @@ def lib():
         L.dphlm_host_free.argtypes = [ctypes.c_void_p]
         L.dphlm_host_free.restype = None
         L.dphlm_device_count.restype = ctypes.c_int
+        L.dphlm_last_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float * 2)]
+        L.dphlm_last_kernel_ms.restype = ctypes.c_int
         L.dphlm_version.restype = ctypes.c_int
         L.dphlm_last_error.restype = ctypes.c_char_p
         _lib = L
     return _lib
+
+
+FLAG_TIMING = 1
+
+
+def last_kernel_ms():
+    """(pre-fit ms, lm() ms) of this thread's last timed device call; blocks until it has finished."""
+    ms = (ctypes.c_float * 2)()
+    if lib().dphlm_last_kernel_ms(ctypes.byref(ms)) != 0:
+        raise RuntimeError("dphlm: " + last_error())
+    return float(ms[0]), float(ms[1])
 
 
 def last_error():

@@ -2,6 +2,7 @@
 // The kernels themselves are lm_launch.cuh (template) instantiated per model in lm_inst_*.cu.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -18,6 +19,12 @@ int fail(const std::string& m) { g_err = m; return -1; }
 namespace {
 
 DeviceCtx g_ctx[64];
+
+struct TimingEvents {
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool valid = false;
+};
+thread_local TimingEvents g_timing;
 
 int get_ctx(int dev, DeviceCtx** out) {
     if (dev < 0 || dev >= 64) return fail("device index out of range");
@@ -67,7 +74,35 @@ int validate(const dphlm_desc* d) {
     return 0;
 }
 
-int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s) {
+// `ws` (optional): caller-provided device workspace of at least workspace_bytes(d)
+size_t workspace_bytes(const dphlm_desc* d) {
+    return (((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255)) + (d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float));
+}
+
+int launch_model(const dphlm_desc* d, int G, const KArgs& a, DeviceCtx* ctx, cudaStream_t s) {
+    const bool mle = d->method == DPHLM_MLE;
+    switch (d->model) {
+        case DPHLM_GAUSS2D: return launch_gauss2d(G, mle, a, ctx, s);
+        case DPHLM_GAUSS2D_ELLIPTICAL: return launch_gauss2d_elliptical(G, mle, a, ctx, s);
+        case DPHLM_MULTI_EXP:
+            switch (d->n_param / 2) {
+                case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, ctx, s);
+                case 2: return launch_multi_exp2(d->n_param & 1, G, mle, a, ctx, s);
+                case 3: return launch_multi_exp3(d->n_param & 1, G, mle, a, ctx, s);
+            }
+    }
+    return fail("unsupported model / n_param");
+}
+
+// Enqueue both kernels for a batch whose buffers are on the device.  A large batch is cut into kParts
+// sub-batches that go to the caller's stream and to auxiliary streams forked from / joined back into it:
+// the kernels are persistent and end only when their slowest fit has converged (pre-fits of 30-80
+// evaluations exist), so one launch pair per batch leaves most SMs idle during two long tails; with
+// sub-batches on concurrent streams the next kernel's CTAs take over the SM slots as they drain.
+constexpr int kParts = 4;
+constexpr long long kSplitMin = 32768;
+
+int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in = nullptr, bool allow_split = true) {
     if (d->n_fits == 0) return 0;
     KArgs a{};
     a.data = d->data; a.xaxis = d->xaxis; a.p0 = d->p0;
@@ -75,28 +110,55 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s) {
     a.p_ls = d->p_ls; a.counts = d->counts;
     a.n_fits = d->n_fits; a.h = d->dim0; a.w = d->dim1;
     a.opt = Options{d->ftol, d->xtol, d->gtol, d->factor, d->maxfev};
+    const bool timing = d->flags & DPHLM_FLAG_TIMING;
+    if (timing) {
+        for (auto& e : g_timing.ev)
+            if (!e) CUDA_TRY(cudaEventCreate(&e));
+        a.ev = g_timing.ev;
+        g_timing.valid = true;
+    }
     const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w);
-    const bool mle = d->method == DPHLM_MLE;
     // workspace: pre-fit exit codes, and the pre-fit parameters when the caller does not want them
     const size_t b_ier = ((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255);
     const size_t b_pls = d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float);
-    char* ws = nullptr;
-    CUDA_TRY(cudaMallocAsync(&ws, b_ier + b_pls, s));
+    char* ws = ws_in;
+    if (!ws) CUDA_TRY(cudaMallocAsync(&ws, b_ier + b_pls, s));
     a.ier = reinterpret_cast<int*>(ws);
     if (!d->p_ls) a.p_ls = reinterpret_cast<float*>(ws + b_ier);
-    int rc = -1;
-    switch (d->model) {
-        case DPHLM_GAUSS2D: rc = launch_gauss2d(G, mle, a, ctx, s); break;
-        case DPHLM_GAUSS2D_ELLIPTICAL: rc = launch_gauss2d_elliptical(G, mle, a, ctx, s); break;
-        case DPHLM_MULTI_EXP:
-            switch (d->n_param / 2) {
-                case 1: rc = launch_multi_exp1(d->n_param & 1, G, mle, a, ctx, s); break;
-                case 2: rc = launch_multi_exp2(d->n_param & 1, G, mle, a, ctx, s); break;
-                case 3: rc = launch_multi_exp3(d->n_param & 1, G, mle, a, ctx, s); break;
+    int rc = 0;
+    const bool split = allow_split && !timing && d->n_fits >= kSplitMin && !(d->flags & DPHLM_FLAG_NO_SPLIT);
+    if (!split) {
+        rc = launch_model(d, G, a, ctx, s);
+    } else {
+        std::lock_guard<std::mutex> lk(ctx->fork_mu);  // the auxiliary streams and events are shared per device
+        if (!ctx->fork_ev) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+            for (int k = 0; k < kParts - 1; ++k) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
             }
-            break;
+        }
+        CUDA_TRY(cudaEventRecord(ctx->fork_ev, s));
+        const long long M = (long long)a.h * a.w, P = d->n_param;
+        const long long per = (d->n_fits + kParts - 1) / kParts;
+        for (int k = 0; k < kParts && rc == 0; ++k) {
+            const long long lo = k * per, n = d->n_fits - lo < per ? d->n_fits - lo : per;
+            if (n <= 0) break;
+            KArgs b = a;
+            b.n_fits = n;
+            b.data += lo * M; b.p0 += lo * P; b.popt += lo * P; b.p_ls += lo * P;
+            b.info += lo; b.nfev += lo; b.chisq += lo; b.ier += lo;
+            if (b.counts) b.counts += 4 * lo;
+            cudaStream_t st = k == 0 ? s : ctx->aux[k - 1];
+            if (k > 0) CUDA_TRY(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+            rc = launch_model(d, G, b, ctx, st);
+            if (k > 0 && rc == 0) {
+                CUDA_TRY(cudaEventRecord(ctx->join_ev[k - 1], st));
+                CUDA_TRY(cudaStreamWaitEvent(s, ctx->join_ev[k - 1], 0));
+            }
+        }
     }
-    cudaFreeAsync(ws, s);
+    if (!ws_in) cudaFreeAsync(ws, s);
     return rc;
 }
 
@@ -134,13 +196,16 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     DeviceCtx* ctx;
     if (get_ctx(device, &ctx)) return -1;
     const size_t M = (size_t)d->dim0 * d->dim1, P = d->n_param;
-    // chunking: >= 4 chunks for overlap once the batch is large, each at most 256k fits
-    long long chunk = d->n_fits / 8;
-    if (chunk < 32768) chunk = 32768;
+    // chunking: about 4 chunks in flight over 3 streams so that copies overlap kernels and the tail of one
+    // chunk's kernel overlaps the head of the next; DPHLM_CHUNK overrides (tuning)
+    long long chunk = (d->n_fits + 3) / 4;
+    if (chunk < 16384) chunk = 16384;
     if (chunk > 262144) chunk = 262144;
+    if (const char* e = getenv("DPHLM_CHUNK")) { long long v = atoll(e); if (v > 0) chunk = v; }
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
                  b_cnt = align_up(chunk * 16), b_x = align_up(M * 4);
-    const size_t need = b_data + 3 * b_par + 3 * b_i + b_cnt + b_x;
+    const size_t b_ws = align_up(chunk * 4) + align_up(chunk * P * 4);
+    const size_t need = b_data + 3 * b_par + 3 * b_i + b_cnt + b_x + b_ws;
     int rc = 0;
     // one host call at a time per device: the staging slots are shared
     static std::mutex host_mu[64];
@@ -169,15 +234,16 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         int* dnfev = (int*)b; b += b_i;
         float* dchi = (float*)b; b += b_i;
         int* dcnt = (int*)b; b += b_cnt;
-        float* dx = (float*)b;
+        float* dx = (float*)b; b += b_x;
+        char* dws = b;
         CUDA_TRY(cudaMemcpyAsync(ddata, d->data + lo * M, n * M * 4, cudaMemcpyHostToDevice, s.stream));
         CUDA_TRY(cudaMemcpyAsync(dp0, d->p0 + lo * P, n * P * 4, cudaMemcpyHostToDevice, s.stream));
         if (d->xaxis) CUDA_TRY(cudaMemcpyAsync(dx, d->xaxis, M * 4, cudaMemcpyHostToDevice, s.stream));
         c.data = ddata; c.p0 = dp0; c.xaxis = d->xaxis ? dx : nullptr;
         c.popt = dpopt; c.info = dinfo; c.nfev = dnfev; c.chisq = dchi;
-        c.p_ls = d->p_ls ? dpls : nullptr;
+        c.p_ls = dpls;  // always materialised in the slot buffer: the lm() kernel starts from it
         c.counts = d->counts ? dcnt : nullptr;
-        rc = fit_device(&c, ctx, s.stream);
+        rc = fit_device(&c, ctx, s.stream, dws, false);
         if (rc) break;
         CUDA_TRY(cudaMemcpyAsync(d->popt + lo * P, dpopt, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->info + lo, dinfo, n * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -205,6 +271,14 @@ void* dphlm_host_alloc(size_t bytes) {
 
 void dphlm_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+int dphlm_last_kernel_ms(float ms[2]) {
+    if (!ms || !g_timing.valid) return fail("no timed dphlm_fit_batch call on this thread");
+    CUDA_TRY(cudaEventSynchronize(g_timing.ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[0], g_timing.ev[0], g_timing.ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[1], g_timing.ev[1], g_timing.ev[2]));
+    return 0;
 }
 
 int dphlm_device_count(void) {

@@ -13,8 +13,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <map>
 #include <mutex>
 #include <string>
+#include <utility>
 
 #include "lm_core.cuh"
 
@@ -49,6 +51,7 @@ struct KArgs {
     long long n_fits;
     int h, w;
     Options opt;
+    cudaEvent_t* ev;  // host-side only: 3 events around the two kernels when timing is requested, else null
 };
 
 constexpr int kWarps = DPH_WARPS;
@@ -61,30 +64,76 @@ __host__ __device__ inline int padded_stride(int M, int G) {
 }
 
 #if defined(__CUDACC__)
-// Fit supply / result sink of the pre-fit kernel.
-template <class Mo, int G>
-struct IoPrefit {
+// ---- double-buffered staging of the next fit's inputs (cp.async, 4-byte granularity: ROIs of 121 floats
+// are only 4-byte aligned in the batch).  While a group iterates on one fit, the ROI, the start
+// parameters and the pre-fit exit code of the fit it will run next are already on their way into the
+// group's second shared-memory buffer.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int kStageExtra = 8;  // floats after the staged ROI: start parameters (<= 7) and one int
+
+template <class Mo, int G, bool MAIN, bool MLE>
+struct IoDevice {
     const KArgs& a;
-    __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, float* pstart, long long& fit) const {
+    float* ynext;          // staging buffer [stride + kStageExtra] of this group
+    long long next = -1;   // index of the staged fit, -1: nothing staged yet
+
+    // claim the next fit index for this group and start copying its inputs
+    __device__ void stage(const Lanes<G>& ln, int M, int stride) {
         constexpr int P = Mo::P;
         const int src = __ffs(ln.gmask) - 1;
+        unsigned long long idx = 0;
+        if (ln.lane == 0) idx = atomicAdd(a.counter, 1ull);
+        idx = __shfl_sync(ln.gmask, idx, src);
+        next = (long long)idx;
+        if (next >= a.n_fits) return;
+        const float* d = a.data + idx * M;
+        for (int i = ln.lane; i < M; i += G) cp_async4(ynext + i, d + i);
+        const float* ps = (MAIN ? a.p_ls : a.p0) + idx * P;
+        for (int k = ln.lane; k < P; k += G) cp_async4(ynext + stride + k, ps + k);
+        if (MAIN && ln.lane == 0) cp_async4(ynext + stride + 7, a.ier + idx);
+    }
+
+    __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, float* pstart, long long& fit) {
+        constexpr int P = Mo::P;
+        if (next < 0) stage(ln, px.M, px.stride);
         for (;;) {
-            unsigned long long idx = 0;
-            if (ln.lane == 0) idx = atomicAdd(a.counter, 1ull);
-            idx = __shfl_sync(ln.gmask, idx, src);
-            if ((long long)idx >= a.n_fits) return false;
-            const float* d = a.data + idx * px.M;
-            bool bad = false;
-            for (int i = ln.lane; i < px.M; i += G) {
-                float v = __ldg(d + i);
-                bad |= !f_finite(v);
-                px.y[i] = v;
-            }
-#pragma unroll
-            for (int k = 0; k < P; ++k) pstart[k] = __ldg(a.p0 + idx * P + k);
-            bad = __any_sync(ln.gmask, bad);
+            if (next >= a.n_fits) return false;
+            const long long idx = next;
+            cp_async_wait_all();
             __syncwarp(ln.gmask);
-            if (!bad) { fit = (long long)idx; return true; }
+            float* t = px.y; px.y = ynext; ynext = t;  // the staged buffer becomes the working one
+            stage(ln, px.M, px.stride);                 // and the following fit starts loading
+#pragma unroll
+            for (int k = 0; k < P; ++k) pstart[k] = px.y[px.stride + k];
+            if (MAIN) {
+                const int ier = __float_as_int(px.y[px.stride + 7]);
+                if (ier < 1 || ier > 4) {  // the pre-fit failed: report it, do not fit (scipy raises, lm.py:642-644)
+                    if (ln.lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < P; ++k) a.popt[idx * P + k] = pstart[k];
+                        a.info[idx] = ier == 0 ? -99 : -ier;
+                        a.nfev[idx] = 0;
+                        a.chisq[idx] = 0.0f;
+                        if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
+                    }
+                    continue;
+                }
+                if (MLE) {  // data <= 0 -> 0 (lm.py:127)
+                    for (int i = ln.lane; i < px.M; i += G) px.y[i] = clamp_nonneg(px.y[i]);
+                    __syncwarp(ln.gmask);
+                }
+                fit = idx;
+                return true;
+            }
+            bool bad = false;
+            for (int i = ln.lane; i < px.M; i += G) bad |= !f_finite(px.y[i]);
+            bad = __any_sync(ln.gmask, bad);
+            if (!bad) { fit = idx; return true; }
             if (ln.lane == 0) {  // the reference raises ValueError (lm.py:651-652)
                 a.ier[idx] = 100;
 #pragma unroll
@@ -100,43 +149,6 @@ struct IoPrefit {
         a.ier[fit] = st.ier;
         if (a.counts) a.counts[4 * fit] = st.nfev;
     }
-};
-
-// Fit supply / result sink of the main (lm) kernel: starts from the pre-fit results.
-template <class Mo, bool MLE, int G>
-struct IoMain {
-    const KArgs& a;
-    __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, float* pstart, long long& fit) const {
-        constexpr int P = Mo::P;
-        const int src = __ffs(ln.gmask) - 1;
-        for (;;) {
-            unsigned long long idx = 0;
-            if (ln.lane == 0) idx = atomicAdd(a.counter, 1ull);
-            idx = __shfl_sync(ln.gmask, idx, src);
-            if ((long long)idx >= a.n_fits) return false;
-            const int ier = __ldg(a.ier + idx);
-#pragma unroll
-            for (int k = 0; k < P; ++k) pstart[k] = a.p_ls[idx * P + k];
-            if (ier >= 1 && ier <= 4) {
-                const float* d = a.data + idx * px.M;
-                for (int i = ln.lane; i < px.M; i += G) {
-                    float v = __ldg(d + i);
-                    px.y[i] = MLE ? clamp_nonneg(v) : v;  // lm.py:127
-                }
-                __syncwarp(ln.gmask);
-                fit = (long long)idx;
-                return true;
-            }
-            if (ln.lane == 0) {  // the pre-fit failed: report it, do not fit (scipy raises, lm.py:642-644)
-#pragma unroll
-                for (int k = 0; k < P; ++k) a.popt[idx * P + k] = pstart[k];
-                a.info[idx] = ier == 0 ? -99 : -ier;
-                a.nfev[idx] = 0;
-                a.chisq[idx] = 0.0f;
-                if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
-            }
-        }
-    }
     __device__ void store(const Lanes<G>& ln, const StageB<Mo, MLE>& st, long long fit) const {
         if (ln.lane != 0) return;
 #pragma unroll
@@ -147,6 +159,14 @@ struct IoMain {
         if (a.counts) { a.counts[4 * fit + 1] = st.n_acc; a.counts[4 * fit + 2] = st.n_rej; a.counts[4 * fit + 3] = 0; }
     }
 };
+template <class Mo, int G>
+using IoPrefit = IoDevice<Mo, G, false, false>;
+template <class Mo, bool MLE, int G>
+using IoMain = IoDevice<Mo, G, true, MLE>;
+
+// shared-memory floats of one lane group: two data buffers (working + staged, each with the extra
+// words) and the double-buffered exponentials
+__host__ __device__ inline int group_region(int stride, int ne) { return 2 * (stride + kStageExtra) + 2 * ne * stride; }
 
 template <class Stage, class Mo, int G, class IO>
 __global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(const KArgs a) {
@@ -164,11 +184,11 @@ __global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(cons
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G;
-    const int region = stride * (1 + 2 * Mo::NE);
+    const int region = group_region(stride, Mo::NE);
     float* base = smem + 2 * ((M + 1) & ~1) + (warp * FPW + grp) * region;
     Lanes<G> ln{lane % G, G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G))};
-    PixelState<Mo::NE> px{base, base + stride, cxy, M, stride, 0};
-    IO io{a};
+    PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cxy, M, stride, 0};
+    IO io{a, base + stride + kStageExtra};
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
 }
 #endif
@@ -184,6 +204,11 @@ struct DeviceCtx {
         char* buf = nullptr;
         size_t cap = 0;
     } slots[3];
+    // fork/join streams for the sub-batches of one device-path call
+    std::mutex fork_mu;
+    cudaEvent_t fork_ev = nullptr;
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t join_ev[3] = {nullptr, nullptr, nullptr};
 };
 constexpr int kCounterRing = 1024;
 
@@ -191,11 +216,27 @@ template <class Kern>
 int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream) {
     KArgs a = a0;
     if (smem > 227 * 1024) return ::dphlm::fail("ROI too large for the shared-memory layout of this group size");
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int occ = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, smem));
-    if (occ < 1) return ::dphlm::fail("kernel does not fit on an SM");
+    // attribute setup and occupancy query once per (kernel instantiation, device, shared-memory size)
+    struct Cached { size_t smem = 0; int occ = 0; };
+    static std::map<std::pair<const void*, int>, Cached> cache;  // Kern is one function-pointer type for all kernels
+    static std::mutex cache_mu;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int occ;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        Cached& c = cache[std::make_pair(reinterpret_cast<const void*>(kern), dev)];
+        if (c.occ == 0 || c.smem != smem) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            int o = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kWarps * 32, smem));
+            if (o < 1) return ::dphlm::fail("kernel does not fit on an SM");
+            c.smem = smem;
+            c.occ = o;
+        }
+        occ = c.occ;
+    }
     unsigned slot;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -217,10 +258,15 @@ template <class Mo, bool MLE, int G>
 int launch(const KArgs& a, DeviceCtx* ctx, cudaStream_t stream) {
     const int M = a.h * a.w;
     constexpr int FPW = 32 / G;
-    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * padded_stride(M, G) * (1 + 2 * Mo::NE));
+    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE));
+    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[0], stream));
     int rc = launch_stage(dphlm_stage_kernel<StageA<Mo>, Mo, G, IoPrefit<Mo, G>>, a, FPW, smem, ctx, stream);
     if (rc) return rc;
-    return launch_stage(dphlm_stage_kernel<StageB<Mo, MLE>, Mo, G, IoMain<Mo, MLE, G>>, a, FPW, smem, ctx, stream);
+    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
+    rc = launch_stage(dphlm_stage_kernel<StageB<Mo, MLE>, Mo, G, IoMain<Mo, MLE, G>>, a, FPW, smem, ctx, stream);
+    if (rc) return rc;
+    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));
+    return 0;
 }
 
 // one per model family, defined in lm_inst_*.cu

@@ -67,7 +67,7 @@ def _check(rc):
 
 
 def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
-                    factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None):
+                    factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None, timing=False, out=None):
     """Fit ``N`` independent ROIs / histograms: the batched form of per-ROI
     ``curve_fit(model, xdata, roi.ravel(), p0, jac=model.jac, method=method)`` (``lm.py:510-685``).
 
@@ -79,6 +79,9 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         tensor goes through the host entry point (copies overlap the kernels; results are numpy arrays).
     p0 : ``[N, P]`` float32 initial guesses.
     xdata : ``multi_exp`` only: the shared ``[M]`` x axis.
+    timing : device path only: record CUDA events around the two kernels (``_lib.last_kernel_ms()``).
+    out : host path only: a ``BatchResult`` of preallocated C-contiguous arrays to write into (use
+        :func:`pinned_empty` buffers, for the inputs too, so that the copies run asynchronously).
     device : host path only: CUDA device index, or a list of indices to shard the batch over several
         GPUs (contiguous shards, one host thread per device, no collective).
 
@@ -90,7 +93,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     one_d = model.model_id == models.MODEL_MULTI_EXP
     if _is_torch(data) and data.is_cuda:
         return _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
-                           return_counts, group_lanes)
+                           return_counts, group_lanes, timing)
     if _is_torch(data):
         data = data.numpy()
     if _is_torch(p0):
@@ -109,10 +112,17 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         xa = np.ascontiguousarray(xdata, dtype=np.float32)
         if xa.shape != (dim0,):
             raise ValueError("xdata must have shape (M,)")
-    out = BatchResult(
-        np.empty((n, n_param), np.float32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32),
-        np.empty((n, n_param), np.float32) if return_stage1 else None, np.empty((n, 4), np.int32) if return_counts else None,
-    )
+    if out is None:
+        out = BatchResult(
+            np.empty((n, n_param), np.float32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32),
+            np.empty((n, n_param), np.float32) if return_stage1 else None, np.empty((n, 4), np.int32) if return_counts else None,
+        )
+    else:
+        want = [((n, n_param), np.float32), ((n,), np.int32), ((n,), np.int32), ((n,), np.float32),
+                ((n, n_param), np.float32) if return_stage1 else None, ((n, 4), np.int32) if return_counts else None]
+        for a, w in zip(out, want):
+            if w is not None and (a is None or a.shape != w[0] or a.dtype != w[1] or not a.flags.c_contiguous):
+                raise ValueError("out: expected a C-contiguous %s array of shape %s" % (np.dtype(w[1]).name, w[0]))
     devices = [0] if device is None else ([device] if isinstance(device, int) else list(device))
 
     def run(dev, lo, hi):
@@ -145,7 +155,30 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     return out
 
 
-def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1, return_counts, group_lanes):
+class _PinnedBlock:
+    """Page-locked host memory from ``dphlm_host_alloc``, released when the last array viewing it dies."""
+
+    def __init__(self, nbytes):
+        self.ptr = _lib.lib().dphlm_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("dphlm_host_alloc(%d) failed: %s" % (nbytes, _lib.last_error()))
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            _lib.lib().dphlm_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """``numpy.empty`` in page-locked host memory: copies to and from it overlap the kernels."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+    return np.asarray(_PinnedBlock(nbytes))[: int(np.prod(shape)) * np.dtype(dtype).itemsize].view(dtype).reshape(shape)
+
+
+def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1, return_counts, group_lanes,
+                timing=False):
     import torch
 
     if data.dtype != torch.float32 or not data.is_contiguous():
@@ -175,6 +208,7 @@ def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev,
     d.popt, d.info, d.nfev, d.chisq = popt.data_ptr(), info.data_ptr(), nfev.data_ptr(), chisq.data_ptr()
     d.p_ls = p_ls.data_ptr() if return_stage1 else None
     d.counts = counts.data_ptr() if return_counts else None
+    d.flags = _lib.FLAG_TIMING if timing else 0
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _check(_lib.lib().dphlm_fit_batch(ctypes.byref(d), ctypes.c_void_p(stream)))

@@ -53,8 +53,14 @@ typedef struct dphlm_desc {
     int32_t* counts;     /* optional [n_fits, 4]: pre-fit evaluations, accepted, rejected steps, 0      */
     float ftol, xtol, gtol, factor; /* lm()/leastsq keywords, forwarded to both stages (lm.py:643, 668) */
     int32_t maxfev;      /* <= 0: 100 * (n_param + 1)                                   (lm.py:306-307) */
-    int32_t flags;       /* reserved, 0 */
+    int32_t flags;       /* DPHLM_FLAG_* */
 } dphlm_desc;
+
+/* flags: record CUDA events around the two kernels of dphlm_fit_batch (read with dphlm_last_kernel_ms) */
+#define DPHLM_FLAG_TIMING 1
+/* flags: keep a device-path batch in one launch pair on the caller's stream (default: batches of >= 32768
+ * fits are cut into 4 sub-batches on internal streams forked from and joined back into the caller's) */
+#define DPHLM_FLAG_NO_SPLIT 2
 
 /* Fill the tolerances with the reference defaults (ftol = xtol = 1.49012e-8, gtol = 0, factor = 100,
  * maxfev = 0 -> 100 (P + 1); dphtools/utils/lm.py:228-233) and zero everything else. */
@@ -73,7 +79,10 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device);
 void* dphlm_host_alloc(size_t bytes);
 void dphlm_host_free(void* p);
 
-/* Useful-work accounting of the last dphlm_fit_batch_host / diagnostics */
+/* Durations (ms, CUDA events on the launch stream) of the pre-fit kernel and of the lm() kernel of this
+ * thread's last dphlm_fit_batch call that had DPHLM_FLAG_TIMING set; waits for that call to finish. */
+int dphlm_last_kernel_ms(float ms[2]);
+
 int dphlm_device_count(void);
 int dphlm_version(void);
 const char* dphlm_last_error(void);
