@@ -61,6 +61,12 @@ def _fill_desc(model, method, n_param, dim0, dim1, n_fits, ftol, xtol, gtol, max
     return d
 
 
+def shard_bounds(n, parts):
+    """Contiguous split of ``n`` fits over ``parts`` devices / ranks: ``[(lo, hi), ...]``."""
+    edges = [(n * k) // parts for k in range(parts + 1)]
+    return list(zip(edges[:-1], edges[1:]))
+
+
 def _check(rc):
     if rc != 0:
         raise RuntimeError("dphlm: " + _lib.last_error())
@@ -137,11 +143,11 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     if len(devices) == 1:
         _check(run(devices[0], 0, n))
     else:  # contiguous shards, one host thread per device; ctypes releases the GIL
-        bounds = np.linspace(0, n, len(devices) + 1).astype(np.int64)
+        bounds = shard_bounds(n, len(devices))
         errs = []
 
         def worker(i):
-            rc = run(devices[i], int(bounds[i]), int(bounds[i + 1]))
+            rc = run(devices[i], *bounds[i])
             if rc:
                 errs.append(_lib.last_error())
 
