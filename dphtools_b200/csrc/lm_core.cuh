@@ -635,7 +635,7 @@ struct StageA {
     float chi;  // 0.5 * fnorm^2
     float par, delta, xnorm, pnorm;
     int ier, nfev;
-    bool init, first;
+    bool init, first, resumed;
 
     DPH_HD void start(const float* p0) {
 #pragma unroll
@@ -643,7 +643,26 @@ struct StageA {
         Mo::prepare(x, q0);
         par = delta = xnorm = pnorm = chi = 0.0f;
         ier = 0; nfev = 0;
-        init = true; first = true;
+        init = true; first = true; resumed = false;
+    }
+    // Continuation record: everything a different lane group needs to carry this fit on from the last
+    // accepted point (A and g are recomputed there by a zero-step pass).
+    static constexpr int kRecord = 2 * P + 6;
+    DPH_HD int trips() const { return nfev; }
+    DPH_HD void save(float* r) const {
+#pragma unroll
+        for (int i = 0; i < P; ++i) { r[i] = x[i]; r[P + i] = D[i]; }
+        r[2 * P] = chi; r[2 * P + 1] = par; r[2 * P + 2] = delta; r[2 * P + 3] = xnorm;
+        r[2 * P + 4] = float(nfev); r[2 * P + 5] = first ? 1.0f : 0.0f;
+    }
+    DPH_HD void resume(const float* r) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) { x[i] = r[i]; D[i] = r[P + i]; }
+        chi = r[2 * P]; par = r[2 * P + 1]; delta = r[2 * P + 2]; xnorm = r[2 * P + 3];
+        nfev = int(r[2 * P + 4]); first = r[2 * P + 5] != 0.0f;
+        Mo::prepare(x, q0);
+        pnorm = 0.0f; ier = 0;
+        init = true; resumed = true;
     }
     DPH_HD bool wants_chi() const { return false; }
     // returns false when the fit ended without needing the pass
@@ -673,6 +692,15 @@ struct StageA {
     DPH_HD bool consume(const Options& opt, const Normal<P>& n, const float* p, const typename Mo::Par& q1, bool& accepted) {
         const int maxfev = opt.maxfev > 0 ? opt.maxfev : 100 * (P + 1);
         accepted = false;
+        if (init && resumed) {  // carried over from another group: only the normal equations are rebuilt
+            init = resumed = false;
+#pragma unroll
+            for (int i = 0; i < NTP; ++i) A[i] = n.A[i];
+#pragma unroll
+            for (int i = 0; i < P; ++i) g[i] = n.g[i];
+            accepted = true;
+            return false;
+        }
         if (init) {
             init = false;
             nfev = 1;
@@ -752,7 +780,7 @@ struct StageB {
     typename Mo::Par q0;
     float chisq_old, chisq_ret, lam;
     int info, ev, n_acc, n_rej;
-    bool init, live;
+    bool init, live, resumed;
 
     DPH_HD void start(const float* p_ls) {
 #pragma unroll
@@ -760,9 +788,26 @@ struct StageB {
         Mo::prepare(x, q0);
         chisq_old = chisq_ret = lam = 0.0f;
         info = 5; ev = 0; n_acc = n_rej = 0;
-        init = true; live = false;
+        init = true; live = false; resumed = false;
     }
-    DPH_HD bool wants_chi() const { return init; }
+    static constexpr int kRecord = 3 * P + 6;
+    DPH_HD int trips() const { return ev; }
+    DPH_HD void save(float* r) const {
+#pragma unroll
+        for (int i = 0; i < P; ++i) { r[i] = x[i]; r[P + i] = dtd[i]; r[2 * P + i] = xret[i]; }
+        r[3 * P] = chisq_old; r[3 * P + 1] = chisq_ret; r[3 * P + 2] = lam;
+        r[3 * P + 3] = float(ev); r[3 * P + 4] = float(n_acc); r[3 * P + 5] = float(n_rej);
+    }
+    DPH_HD void resume(const float* r) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) { x[i] = r[i]; dtd[i] = r[P + i]; xret[i] = r[2 * P + i]; }
+        chisq_old = r[3 * P]; chisq_ret = r[3 * P + 1]; lam = r[3 * P + 2];
+        ev = int(r[3 * P + 3]); n_acc = int(r[3 * P + 4]); n_rej = int(r[3 * P + 5]);
+        Mo::prepare(x, q0);
+        info = 5;
+        init = true; live = false; resumed = true;
+    }
+    DPH_HD bool wants_chi() const { return init && !resumed; }
     DPH_HD bool propose(const Options& opt, float* p) {
         live = false;
 #pragma unroll
@@ -800,6 +845,15 @@ struct StageB {
     DPH_HD bool consume(const Options& opt, const Normal<P>& n, const float* p, const typename Mo::Par& q1, bool& accepted) {
         const int maxfev = opt.maxfev > 0 ? opt.maxfev : 100 * (P + 1);
         accepted = false;
+        if (init && resumed) {
+            init = resumed = false;
+#pragma unroll
+            for (int i = 0; i < NTP; ++i) A[i] = n.A[i];
+#pragma unroll
+            for (int i = 0; i < P; ++i) g[i] = n.g[i];
+            accepted = true;
+            return false;
+        }
         if (init) {
             init = false;
 #pragma unroll
@@ -857,7 +911,10 @@ struct StageB {
 // Runs one stage for a stream of fits.  Every lane group owns one fit at a time and fetches the next one
 // from `io` as soon as its own has finished, so the groups of a warp never wait for each other's
 // iteration counts; the only warp-wide operations (the shuffles of the pass reductions) sit at
-// warp-uniform points of the loop.  `io` supplies fits (fetch) and takes results (store).
+// warp-uniform points of the loop.  `io` supplies fits (fetch: start or resume `st`), takes results (store)
+// and may take over a fit that has used up its trip budget (park): stragglers -- the reference's own
+// trajectories reach 100-360 trips on degenerate ROIs -- are handed to a follow-up launch where a whole
+// warp owns each fit, instead of holding a narrow group (and the tail of the kernel) for milliseconds.
 template <class Stage, class Mo, int G, class IO>
 DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options& opt, IO& io) {
     constexpr int P = Mo::P;
@@ -874,9 +931,7 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
     for (;;) {
         if (Lanes<G>::warp_any(!has && !exhausted)) {
             if (!has && !exhausted) {
-                float pstart[P];
-                if (io.fetch(ln, px, pstart, fit)) {
-                    st.start(pstart);
+                if (io.fetch(ln, px, st, fit)) {
                     px.cur = 0;
                     has = true;
                 } else {
@@ -913,6 +968,8 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
             if (accepted) px.cur = 1 - px.cur;
             if (done) {
                 io.store(ln, st, fit);
+                has = false;
+            } else if (st.trips() >= io.budget() && io.park(ln, st, fit)) {
                 has = false;
             }
         }

@@ -75,8 +75,19 @@ int validate(const dphlm_desc* d) {
 }
 
 // `ws` (optional): caller-provided device workspace of at least workspace_bytes(d)
+int park_capacity(long long n) {
+    long long c = n / 16;
+    if (c < 256) c = 256;
+    if (c > 65536) c = 65536;
+    return (int)c;
+}
+size_t park_bytes(long long n) {  // two stages: count, indices, records
+    const size_t cap = park_capacity(n);
+    return 256 + 2 * cap * sizeof(int) + 2 * cap * kParkRecord * sizeof(float);
+}
 size_t workspace_bytes(const dphlm_desc* d) {
-    return (((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255)) + (d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float));
+    return (((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255)) + park_bytes(d->n_fits) +
+           (d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float));
 }
 
 int launch_model(const dphlm_desc* d, int G, const KArgs& a, DeviceCtx* ctx, cudaStream_t s) {
@@ -94,15 +105,8 @@ int launch_model(const dphlm_desc* d, int G, const KArgs& a, DeviceCtx* ctx, cud
     return fail("unsupported model / n_param");
 }
 
-// Enqueue both kernels for a batch whose buffers are on the device.  A large batch is cut into kParts
-// sub-batches that go to the caller's stream and to auxiliary streams forked from / joined back into it:
-// the kernels are persistent and end only when their slowest fit has converged (pre-fits of 30-80
-// evaluations exist), so one launch pair per batch leaves most SMs idle during two long tails; with
-// sub-batches on concurrent streams the next kernel's CTAs take over the SM slots as they drain.
-constexpr int kParts = 4;
-constexpr long long kSplitMin = 32768;
-
-int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in = nullptr, bool allow_split = true) {
+// Enqueue the kernels for a batch whose buffers are on the device.
+int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in = nullptr) {
     if (d->n_fits == 0) return 0;
     KArgs a{};
     a.data = d->data; a.xaxis = d->xaxis; a.p0 = d->p0;
@@ -110,8 +114,7 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     a.p_ls = d->p_ls; a.counts = d->counts;
     a.n_fits = d->n_fits; a.h = d->dim0; a.w = d->dim1;
     a.opt = Options{d->ftol, d->xtol, d->gtol, d->factor, d->maxfev};
-    const bool timing = d->flags & DPHLM_FLAG_TIMING;
-    if (timing) {
+    if (d->flags & DPHLM_FLAG_TIMING) {
         for (auto& e : g_timing.ev)
             if (!e) CUDA_TRY(cudaEventCreate(&e));
         a.ev = g_timing.ev;
@@ -120,43 +123,29 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w);
     // workspace: pre-fit exit codes, and the pre-fit parameters when the caller does not want them
     const size_t b_ier = ((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255);
+    const size_t b_park = park_bytes(d->n_fits);
     const size_t b_pls = d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float);
     char* ws = ws_in;
-    if (!ws) CUDA_TRY(cudaMallocAsync(&ws, b_ier + b_pls, s));
+    if (!ws) CUDA_TRY(cudaMallocAsync(&ws, b_ier + b_park + b_pls, s));
     a.ier = reinterpret_cast<int*>(ws);
-    if (!d->p_ls) a.p_ls = reinterpret_cast<float*>(ws + b_ier);
-    int rc = 0;
-    const bool split = allow_split && !timing && d->n_fits >= kSplitMin && !(d->flags & DPHLM_FLAG_NO_SPLIT);
-    if (!split) {
+    if (!d->p_ls) a.p_ls = reinterpret_cast<float*>(ws + b_ier + b_park);
+    // straggler lists (DPHLM_FLAG_NO_HANDOFF: keep every fit in the group that started it)
+    a.park_cap = (d->flags & DPHLM_FLAG_NO_HANDOFF) ? 0 : park_capacity(d->n_fits);
+    a.park_count = reinterpret_cast<int*>(ws + b_ier);
+    a.park_idx = a.park_count + 64;
+    a.park_rec = reinterpret_cast<float*>(a.park_idx + 2 * (size_t)park_capacity(d->n_fits));
+    CUDA_TRY(cudaMemsetAsync(a.park_count, 0, 256, s));
+    int rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->fork_mu);  // the side stream and its events are shared per device
+        if (!ctx->sides[0].stream) {
+            for (auto& sd : ctx->sides) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&sd.fork_ev, cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&sd.join_ev, cudaEventDisableTiming));
+            }
+        }
         rc = launch_model(d, G, a, ctx, s);
-    } else {
-        std::lock_guard<std::mutex> lk(ctx->fork_mu);  // the auxiliary streams and events are shared per device
-        if (!ctx->fork_ev) {
-            CUDA_TRY(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-            for (int k = 0; k < kParts - 1; ++k) {
-                CUDA_TRY(cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
-                CUDA_TRY(cudaEventCreateWithFlags(&ctx->join_ev[k], cudaEventDisableTiming));
-            }
-        }
-        CUDA_TRY(cudaEventRecord(ctx->fork_ev, s));
-        const long long M = (long long)a.h * a.w, P = d->n_param;
-        const long long per = (d->n_fits + kParts - 1) / kParts;
-        for (int k = 0; k < kParts && rc == 0; ++k) {
-            const long long lo = k * per, n = d->n_fits - lo < per ? d->n_fits - lo : per;
-            if (n <= 0) break;
-            KArgs b = a;
-            b.n_fits = n;
-            b.data += lo * M; b.p0 += lo * P; b.popt += lo * P; b.p_ls += lo * P;
-            b.info += lo; b.nfev += lo; b.chisq += lo; b.ier += lo;
-            if (b.counts) b.counts += 4 * lo;
-            cudaStream_t st = k == 0 ? s : ctx->aux[k - 1];
-            if (k > 0) CUDA_TRY(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
-            rc = launch_model(d, G, b, ctx, st);
-            if (k > 0 && rc == 0) {
-                CUDA_TRY(cudaEventRecord(ctx->join_ev[k - 1], st));
-                CUDA_TRY(cudaStreamWaitEvent(s, ctx->join_ev[k - 1], 0));
-            }
-        }
     }
     if (!ws_in) cudaFreeAsync(ws, s);
     return rc;
@@ -178,8 +167,11 @@ void dphlm_desc_init(dphlm_desc* d) {
     d->maxfev = 0;
 }
 
-int dphlm_fit_batch(const dphlm_desc* d, void* stream) {
-    if (validate(d)) return -1;
+int dphlm_fit_batch(const dphlm_desc* d_in, void* stream) {
+    if (validate(d_in)) return -1;
+    dphlm_desc tuned = *d_in;  // DPHLM_FLAGS (environment) ORs extra flags in: tuning aid
+    if (const char* e = getenv("DPHLM_FLAGS")) tuned.flags |= atoi(e);
+    const dphlm_desc* d = &tuned;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     DeviceCtx* ctx;
@@ -204,7 +196,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     if (const char* e = getenv("DPHLM_CHUNK")) { long long v = atoll(e); if (v > 0) chunk = v; }
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
                  b_cnt = align_up(chunk * 16), b_x = align_up(M * 4);
-    const size_t b_ws = align_up(chunk * 4) + align_up(chunk * P * 4);
+    const size_t b_ws = align_up(chunk * 4) + align_up(park_bytes(chunk)) + align_up(chunk * P * 4);
     const size_t need = b_data + 3 * b_par + 3 * b_i + b_cnt + b_x + b_ws;
     int rc = 0;
     // one host call at a time per device: the staging slots are shared
@@ -243,7 +235,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         c.popt = dpopt; c.info = dinfo; c.nfev = dnfev; c.chisq = dchi;
         c.p_ls = dpls;  // always materialised in the slot buffer: the lm() kernel starts from it
         c.counts = d->counts ? dcnt : nullptr;
-        rc = fit_device(&c, ctx, s.stream, dws, false);
+        rc = fit_device(&c, ctx, s.stream, dws);
         if (rc) break;
         CUDA_TRY(cudaMemcpyAsync(d->popt + lo * P, dpopt, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->info + lo, dinfo, n * 4, cudaMemcpyDeviceToHost, s.stream));

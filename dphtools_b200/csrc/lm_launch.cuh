@@ -48,6 +48,12 @@ struct KArgs {
     int* ier;      // workspace [n_fits]: exit code of the pre-fit (100 = non-finite input data)
     int* counts;   // optional
     unsigned long long* counter;
+    // straggler hand-off: fits that used up `budget` trips are parked here and resumed by a warp-per-fit launch
+    int* park_count;   // [1] number of parked fits of this stage (may exceed park_cap: the excess was not parked)
+    int* park_idx;     // [park_cap] fit indices
+    float* park_rec;   // [park_cap][kParkRecord] continuation records (Stage::save)
+    int park_cap;
+    int budget;        // trips before parking; <= 0: never
     long long n_fits;
     int h, w;
     Options opt;
@@ -55,6 +61,8 @@ struct KArgs {
 };
 
 constexpr int kWarps = DPH_WARPS;
+constexpr int kParkRecord = 32;
+constexpr int kIerParked = -1;   // pre-fit exit code of a fit whose pre-fit is still running in the follow-up launch  // floats per continuation record (>= 3 P + 6 for P <= 7)
 
 // per-fit stride of the shared-memory arrays: >= M and congruent to G modulo 32, so that the G-lane
 // groups of a warp touch disjoint banks
@@ -76,11 +84,32 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int kStageExtra = 8;  // floats after the staged ROI: start parameters (<= 7) and one int
 
-template <class Mo, int G, bool MAIN, bool MLE>
+template <class Stage, class Mo, int G, bool MAIN, bool MLE, bool RESUME>
 struct IoDevice {
     const KArgs& a;
     float* ynext;          // staging buffer [stride + kStageExtra] of this group
     long long next = -1;   // index of the staged fit, -1: nothing staged yet
+
+    __device__ int budget() const { return (RESUME || a.budget <= 0) ? 0x7fffffff : a.budget; }
+
+    // hand a fit that has used up its trip budget to the warp-per-fit follow-up launch
+    __device__ bool park(const Lanes<G>& ln, const Stage& st, long long fit) const {
+        if (RESUME) return false;
+        const int src = __ffs(ln.gmask) - 1;
+        int slot = 0;
+        if (ln.lane == 0) slot = atomicAdd(a.park_count, 1);
+        slot = __shfl_sync(ln.gmask, slot, src);
+        if (slot >= a.park_cap) return false;  // list full: the fit simply stays where it is
+        if (ln.lane == 0) {
+            float r[kParkRecord];
+            st.save(r);
+#pragma unroll
+            for (int k = 0; k < Stage::kRecord; ++k) a.park_rec[(size_t)slot * kParkRecord + k] = r[k];
+            a.park_idx[slot] = (int)fit;
+            if (!MAIN) a.ier[fit] = kIerParked;  // the lm() kernel skips it; the follow-up launch runs it once its pre-fit is done
+        }
+        return true;
+    }
 
     // claim the next fit index for this group and start copying its inputs
     __device__ void stage(const Lanes<G>& ln, int M, int stride) {
@@ -98,8 +127,72 @@ struct IoDevice {
         if (MAIN && ln.lane == 0) cp_async4(ynext + stride + 7, a.ier + idx);
     }
 
-    __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, float* pstart, long long& fit) {
+    // resume launch: next parked fit, loaded directly (a handful of fits, a whole warp each)
+    __device__ bool fetch_parked(const Lanes<G>& ln, PixelState<Mo::NE>& px, Stage& st, long long& fit) const {
+        const int src = __ffs(ln.gmask) - 1;
+        unsigned long long slot = 0;
+        if (ln.lane == 0) slot = atomicAdd(a.counter, 1ull);
+        slot = __shfl_sync(ln.gmask, slot, src);
+        int n_parked = *reinterpret_cast<volatile int*>(a.park_count);
+        if (n_parked > a.park_cap) n_parked = a.park_cap;
+        for (;;) {
+            bool fresh = false;
+            long long idx;
+            if ((long long)slot < n_parked) {
+                idx = a.park_idx[slot];
+            } else if (MAIN) {
+                // second list: fits whose PRE-FIT was parked; that has finished by now, start their lm() loop here
+                int n_late = *reinterpret_cast<volatile int*>(a.park_count - 1);
+                if (n_late > a.park_cap) n_late = a.park_cap;
+                const long long j = (long long)slot - n_parked;
+                if (j >= n_late) return false;
+                idx = (a.park_idx - a.park_cap)[j];
+                fresh = true;
+            } else {
+                return false;
+            }
+            if (fresh) {
+                constexpr int P = Mo::P;
+                const int ier = -a.ier[idx] - 2;  // as stored by the resumed pre-fit
+                float pstart[P];
+#pragma unroll
+                for (int k = 0; k < P; ++k) pstart[k] = a.p_ls[idx * P + k];
+                if (ier < 1 || ier > 4) {
+                    if (ln.lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < P; ++k) a.popt[idx * P + k] = pstart[k];
+                        a.info[idx] = ier == 0 ? -99 : -ier;
+                        a.nfev[idx] = 0;
+                        a.chisq[idx] = 0.0f;
+                        if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
+                    }
+                    if (ln.lane == 0) slot = atomicAdd(a.counter, 1ull);
+                    slot = __shfl_sync(ln.gmask, slot, src);
+                    continue;
+                }
+                st.start(pstart);
+            }
+            const float* d = a.data + idx * px.M;
+            for (int i = ln.lane; i < px.M; i += G) {
+                float v = __ldg(d + i);
+                px.y[i] = (MAIN && MLE) ? clamp_nonneg(v) : v;
+            }
+            __syncwarp(ln.gmask);
+            if (!fresh) {
+                float r[kParkRecord];
+#pragma unroll
+                for (int k = 0; k < Stage::kRecord; ++k) r[k] = a.park_rec[(size_t)slot * kParkRecord + k];
+                st.resume(r);
+            }
+            fit = idx;
+            return true;
+        }
+    }
+
+    __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, Stage& st, long long& fit) {
         constexpr int P = Mo::P;
+        if (RESUME) return fetch_parked(ln, px, st, fit);
+        float pstart[P];
         if (next < 0) stage(ln, px.M, px.stride);
         for (;;) {
             if (next >= a.n_fits) return false;
@@ -112,6 +205,7 @@ struct IoDevice {
             for (int k = 0; k < P; ++k) pstart[k] = px.y[px.stride + k];
             if (MAIN) {
                 const int ier = __float_as_int(px.y[px.stride + 7]);
+                if (ier <= kIerParked) continue;  // pre-fit parked: still running (or just finished) in the follow-up launch, which will also run lm()
                 if (ier < 1 || ier > 4) {  // the pre-fit failed: report it, do not fit (scipy raises, lm.py:642-644)
                     if (ln.lane == 0) {
 #pragma unroll
@@ -128,12 +222,13 @@ struct IoDevice {
                     __syncwarp(ln.gmask);
                 }
                 fit = idx;
+                st.start(pstart);
                 return true;
             }
             bool bad = false;
             for (int i = ln.lane; i < px.M; i += G) bad |= !f_finite(px.y[i]);
             bad = __any_sync(ln.gmask, bad);
-            if (!bad) { fit = idx; return true; }
+            if (!bad) { fit = idx; st.start(pstart); return true; }
             if (ln.lane == 0) {  // the reference raises ValueError (lm.py:651-652)
                 a.ier[idx] = 100;
 #pragma unroll
@@ -146,7 +241,8 @@ struct IoDevice {
         if (ln.lane != 0) return;
 #pragma unroll
         for (int k = 0; k < Mo::P; ++k) a.p_ls[fit * Mo::P + k] = st.x[k];
-        a.ier[fit] = st.ier;
+        // a resumed pre-fit ends while the lm() kernel may be reading this array: keep the entry <= kIerParked
+        a.ier[fit] = RESUME ? -st.ier - 2 : st.ier;
         if (a.counts) a.counts[4 * fit] = st.nfev;
     }
     __device__ void store(const Lanes<G>& ln, const StageB<Mo, MLE>& st, long long fit) const {
@@ -159,10 +255,6 @@ struct IoDevice {
         if (a.counts) { a.counts[4 * fit + 1] = st.n_acc; a.counts[4 * fit + 2] = st.n_rej; a.counts[4 * fit + 3] = 0; }
     }
 };
-template <class Mo, int G>
-using IoPrefit = IoDevice<Mo, G, false, false>;
-template <class Mo, bool MLE, int G>
-using IoMain = IoDevice<Mo, G, true, MLE>;
 
 // shared-memory floats of one lane group: two data buffers (working + staged, each with the extra
 // words) and the double-buffered exponentials
@@ -204,16 +296,19 @@ struct DeviceCtx {
         char* buf = nullptr;
         size_t cap = 0;
     } slots[3];
-    // fork/join streams for the sub-batches of one device-path call
+    // side stream for the follow-up launch of the pre-fit stragglers (forked from / joined into the caller's)
+    // (a few, used round-robin, so that concurrent calls on different streams do not serialise behind each other)
     std::mutex fork_mu;
-    cudaEvent_t fork_ev = nullptr;
-    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t join_ev[3] = {nullptr, nullptr, nullptr};
+    struct Side {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    } sides[4];
+    unsigned next_side = 0;
 };
 constexpr int kCounterRing = 1024;
 
 template <class Kern>
-int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream) {
+int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream, long long work = -1) {
     KArgs a = a0;
     if (smem > 227 * 1024) return ::dphlm::fail("ROI too large for the shared-memory layout of this group size");
     // attribute setup and occupancy query once per (kernel instantiation, device, shared-memory size)
@@ -245,7 +340,8 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
     a.counter = ctx->counters + slot;
     CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
     long long grid = (long long)ctx->sms * occ;
-    const long long need = (a.n_fits + (long long)kWarps * fpw - 1) / ((long long)kWarps * fpw);
+    if (work < 0) work = a.n_fits;
+    const long long need = (work + (long long)kWarps * fpw - 1) / ((long long)kWarps * fpw);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
@@ -253,18 +349,47 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
     return 0;
 }
 
-// both stages of curve_fit(method='ls'|'mle') for one batch: pre-fit kernel, then the lm() kernel
+// both stages of curve_fit(method='ls'|'mle') for one batch: pre-fit kernel, then the lm() kernel, each followed
+// by a small warp-per-fit launch that finishes the stragglers the main kernel parked
+constexpr int kBudgetPrefit = 16, kBudgetMain = 24;  // ~p99.9 of the trip counts (mean 7 and 9.7)
+
 template <class Mo, bool MLE, int G>
-int launch(const KArgs& a, DeviceCtx* ctx, cudaStream_t stream) {
-    const int M = a.h * a.w;
+int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
+    const int M = a0.h * a0.w;
     constexpr int FPW = 32 / G;
     const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE));
+    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE));
+    const bool handoff = G < 32 && a0.park_cap > 0 && a0.budget >= 0;
+    using SA = StageA<Mo>;
+    using SB = StageB<Mo, MLE>;
+    KArgs a = a0;
+    a.budget = handoff ? kBudgetPrefit : 0;
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[0], stream));
-    int rc = launch_stage(dphlm_stage_kernel<StageA<Mo>, Mo, G, IoPrefit<Mo, G>>, a, FPW, smem, ctx, stream);
+    int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream);
     if (rc) return rc;
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
-    rc = launch_stage(dphlm_stage_kernel<StageB<Mo, MLE>, Mo, G, IoMain<Mo, MLE, G>>, a, FPW, smem, ctx, stream);
-    if (rc) return rc;
+    // The parked pre-fits (a handful of long ones) and the lm() kernel for everything else run concurrently.
+    // The straggler launch stays on the caller's stream, directly behind the pre-fit kernel, so that its few CTAs
+    // are resident before the persistent lm() kernel -- sent through the side stream -- takes every remaining slot.
+    KArgs b = a;
+    b.budget = handoff ? kBudgetMain : 0;
+    b.park_count += 1; b.park_idx += a.park_cap; b.park_rec += (size_t)a.park_cap * kParkRecord;
+    if (handoff) {
+        DeviceCtx::Side& sd = ctx->sides[ctx->next_side++ % 4];  // the caller holds ctx->fork_mu
+        CUDA_TRY(cudaEventRecord(sd.fork_ev, stream));
+        rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, a, 1, smem_w, ctx, stream, a.park_cap);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamWaitEvent(sd.stream, sd.fork_ev, 0));
+        rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, sd.stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(sd.join_ev, sd.stream));
+        CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_ev, 0));
+        rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, b, 1, smem_w, ctx, stream, 2 * a.park_cap);
+        if (rc) return rc;
+    } else {
+        rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream);
+        if (rc) return rc;
+    }
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));
     return 0;
 }

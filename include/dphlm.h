@@ -58,9 +58,8 @@ typedef struct dphlm_desc {
 
 /* flags: record CUDA events around the two kernels of dphlm_fit_batch (read with dphlm_last_kernel_ms) */
 #define DPHLM_FLAG_TIMING 1
-/* flags: keep a device-path batch in one launch pair on the caller's stream (default: batches of >= 32768
- * fits are cut into 4 sub-batches on internal streams forked from and joined back into the caller's) */
-#define DPHLM_FLAG_NO_SPLIT 2
+/* flags: do not hand stragglers (fits beyond ~p99.9 of the trip counts) to the warp-per-fit follow-up launches */
+#define DPHLM_FLAG_NO_HANDOFF 2
 
 /* Fill the tolerances with the reference defaults (ftol = xtol = 1.49012e-8, gtol = 0, factor = 100,
  * maxfev = 0 -> 100 (P + 1); dphtools/utils/lm.py:228-233) and zero everything else. */

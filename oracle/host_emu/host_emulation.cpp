@@ -9,6 +9,11 @@
 
 using namespace dphlm;
 
+struct Parked {
+    long fit;
+    std::vector<float> rec;
+};
+
 struct Buffers {
     int M;
     long n;
@@ -17,20 +22,41 @@ struct Buffers {
     float *popt, *p_ls, *chisq;
     int *info, *nfev, *counts;
     std::vector<int> ier;
+    int budget;  // trips after which a fit is parked and later resumed (exercises save/resume); 0 = never
+    std::vector<Parked> parked;
+    std::vector<char> was_parked;
 };
 
 template <class Mo>
 struct HostIoPrefit {
     Buffers& b;
     long next = 0;
-    bool fetch(const Lanes<1>&, PixelState<Mo::NE>& px, float* pstart, long long& fit) {
+    size_t resumed = 0;
+    int budget() const { return b.budget > 0 ? b.budget : 1 << 30; }
+    bool park(const Lanes<1>&, const StageA<Mo>& st, long long fit) {
+        if (b.was_parked[fit]) return false;  // park once
+        b.was_parked[fit] = 1;
+        Parked pk{fit, std::vector<float>(StageA<Mo>::kRecord)};
+        st.save(pk.rec.data());
+        b.parked.push_back(pk);
+        return true;
+    }
+    bool fetch(const Lanes<1>&, PixelState<Mo::NE>& px, StageA<Mo>& st, long long& fit) {
+        float pstart[Mo::P];
         for (;;) {
-            if (next >= b.n) return false;
+            if (next >= b.n) {
+                if (resumed >= b.parked.size()) return false;
+                const Parked& pk = b.parked[resumed++];
+                for (int i = 0; i < b.M; ++i) px.y[i] = b.data[pk.fit * b.M + i];
+                st.resume(pk.rec.data());
+                fit = pk.fit;
+                return true;
+            }
             long idx = next++;
             bool bad = false;
             for (int i = 0; i < b.M; ++i) { float v = b.data[idx * b.M + i]; bad |= !std::isfinite(v); px.y[i] = v; }
             for (int k = 0; k < Mo::P; ++k) pstart[k] = b.p0[idx * Mo::P + k];
-            if (!bad) { fit = idx; return true; }
+            if (!bad) { fit = idx; st.start(pstart); return true; }
             b.ier[idx] = 100;
             for (int k = 0; k < Mo::P; ++k) b.p_ls[idx * Mo::P + k] = pstart[k];
             for (int k = 0; k < 4; ++k) b.counts[4 * idx + k] = 0;
@@ -47,15 +73,34 @@ template <class Mo, bool MLE>
 struct HostIoMain {
     Buffers& b;
     long next = 0;
-    bool fetch(const Lanes<1>&, PixelState<Mo::NE>& px, float* pstart, long long& fit) {
+    size_t resumed = 0;
+    int budget() const { return b.budget > 0 ? b.budget : 1 << 30; }
+    bool park(const Lanes<1>&, const StageB<Mo, MLE>& st, long long fit) {
+        if (b.was_parked[fit]) return false;
+        b.was_parked[fit] = 1;
+        Parked pk{fit, std::vector<float>(StageB<Mo, MLE>::kRecord)};
+        st.save(pk.rec.data());
+        b.parked.push_back(pk);
+        return true;
+    }
+    bool fetch(const Lanes<1>&, PixelState<Mo::NE>& px, StageB<Mo, MLE>& st, long long& fit) {
+        float pstart[Mo::P];
         for (;;) {
-            if (next >= b.n) return false;
+            if (next >= b.n) {
+                if (resumed >= b.parked.size()) return false;
+                const Parked& pk = b.parked[resumed++];
+                for (int i = 0; i < b.M; ++i) { float v = b.data[pk.fit * b.M + i]; px.y[i] = MLE ? clamp_nonneg(v) : v; }
+                st.resume(pk.rec.data());
+                fit = pk.fit;
+                return true;
+            }
             long idx = next++;
             int ier = b.ier[idx];
             for (int k = 0; k < Mo::P; ++k) pstart[k] = b.p_ls[idx * Mo::P + k];
             if (ier >= 1 && ier <= 4) {
                 for (int i = 0; i < b.M; ++i) { float v = b.data[idx * b.M + i]; px.y[i] = MLE ? clamp_nonneg(v) : v; }
                 fit = idx;
+                st.start(pstart);
                 return true;
             }
             for (int k = 0; k < Mo::P; ++k) b.popt[idx * Mo::P + k] = pstart[k];
@@ -84,15 +129,17 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
     PixelState<Mo::NE> px{y.data(), e.data(), cxy.data(), M, M, 0};
     HostIoPrefit<Mo> ioa{b};
     run_stage<StageA<Mo>, Mo, 1>(ln, px, opt, ioa);
+    b.parked.clear();
+    b.was_parked.assign(b.n, 0);
     HostIoMain<Mo, MLE> iob{b};
     run_stage<StageB<Mo, MLE>, Mo, 1>(ln, px, opt, iob);
 }
 
 extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, long n, const float* data,
                              const float* xaxis, const float* p0, float ftol, float xtol, float gtol, float factor,
-                             int maxfev, float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts) {
+                             int maxfev, int budget, float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts) {
     Options opt{ftol, xtol, gtol, factor, maxfev};
-    Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0)};
+    Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0), budget, {}, std::vector<char>(n, 0)};
 #define RUN(...)                                                 \
     do {                                                         \
         if (method) run<__VA_ARGS__, true>(h, w, xaxis, opt, b);  \
