@@ -69,6 +69,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.active = False  # set around the timed regions: only those samples count
 
     def run(self):
         try:
@@ -84,13 +85,11 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             }
             while not self.stop_flag:
-                util = nv.nvmlDeviceGetUtilizationRates(h).gpu
-                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                if util > 0:
-                    self.samples.append(mhz)
+                if self.active:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                     self.reasons |= {v for k, v in names.items() if r & k}
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as e:  # NVML missing: report that, never fail the run
             self.reasons.add("nvml_unavailable:" + type(e).__name__)
 
@@ -181,11 +180,13 @@ def main():
         step(i)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active = True
     ev0.record()
     for i in range(args.steps):
         res = step(i)
     ev1.record()
     barrier()
+    sampler.active = False
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -225,11 +226,13 @@ def main():
     for i in range(2):
         dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local, out=h_out)
     barrier()
+    sampler.active = True
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         r_host = dph.curve_fit_batch(models.gauss2d, h_sets[i % 2][0], h_sets[i % 2][1], "mle", device=local, out=h_out)
     barrier()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    sampler.active = False
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t_e2e.item())
@@ -262,7 +265,7 @@ def main():
             "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
-                "traffic": None, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481)",
+                "traffic": None, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; with its straggler follow-up launches)",
                 "kernel_ms": k_main * 1e3, "share_of_step": k_main / k_s,
                 "peak_source": "SMs x 128 lanes x 2 x max SM clock (no fp32 entry in MEASURED_PEAKS.json)",
                 "flops_per_fit": float(np.mean(fl_main)) / n,

@@ -171,9 +171,12 @@ class _PinnedBlock:
         self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
 
     def __del__(self):
-        if getattr(self, "ptr", None):
-            _lib.lib().dphlm_host_free(self.ptr)
-            self.ptr = None
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                _lib.lib().dphlm_host_free(ptr)
+            except Exception:  # interpreter shutdown: the process is going away anyway
+                pass
 
 
 def pinned_empty(shape, dtype=np.float32):
