@@ -58,27 +58,77 @@ constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kInf = __builtin_huge_valf();
 
+// ------------------------------------------------------------------------- packed pairs (f32x2)
+// The pixel passes run on PAIRS of adjacent pixels held in the two halves of a 64-bit register pair and
+// use Blackwell's packed fp32 instructions (SASS FFMA2 / FMUL2 / FADD2, PTX fma.rn.f32x2, sm_100+): one
+// issue slot per two FMAs.  Measured on B200 (scripts/microbench/fp32_peak.cu): scalar FFMA chains reach
+// 42 TFLOP/s, FFMA2 chains 66 TFLOP/s of the nominal 74.  A per-fit scalar used as an operand is encoded
+// as a broadcast source, so splatting costs nothing.  The same templates instantiated with T = float
+// serve the odd tail pixel, the careful (irregular) pass and the host build.
+struct alignas(8) f2 {
+    float x, y;
+    DPH_HD f2() {}
+    DPH_HD f2(float s) : x(s), y(s) {}
+    DPH_HD f2(float a, float b) : x(a), y(b) {}
+};
+#if defined(__CUDA_ARCH__)
+DPH_HD f2 f_fma(f2 a, f2 b, f2 c) {
+    float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    return f2(r.x, r.y);
+}
+DPH_HD f2 operator*(f2 a, f2 b) { float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2(r.x, r.y); }
+DPH_HD f2 operator+(f2 a, f2 b) { float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return f2(r.x, r.y); }
+DPH_HD f2 operator-(f2 a, f2 b) { return f_fma(b, f2(-1.0f), a); }
+#else
+DPH_HD f2 f_fma(f2 a, f2 b, f2 c) { return f2(f_fma(a.x, b.x, c.x), f_fma(a.y, b.y, c.y)); }
+DPH_HD f2 operator*(f2 a, f2 b) { return f2(a.x * b.x, a.y * b.y); }
+DPH_HD f2 operator+(f2 a, f2 b) { return f2(a.x + b.x, a.y + b.y); }
+DPH_HD f2 operator-(f2 a, f2 b) { return f2(a.x - b.x, a.y - b.y); }
+#endif
+// component-wise helpers, defined for float and f2 alike
+DPH_HD float v_ex2(float a) { return f_ex2(a); }
+DPH_HD f2 v_ex2(f2 a) { return f2(f_ex2(a.x), f_ex2(a.y)); }
+DPH_HD float v_rcp(float a) { return f_rcp(a); }
+DPH_HD f2 v_rcp(f2 a) { return f2(f_rcp(a.x), f_rcp(a.y)); }
+DPH_HD float v_lg2(float a) { return f_lg2(a); }
+DPH_HD f2 v_lg2(f2 a) { return f2(f_lg2(a.x), f_lg2(a.y)); }
+DPH_HD float v_max(float a, float b) { return fmaxf(a, b); }
+DPH_HD f2 v_max(f2 a, float b) { return f2(fmaxf(a.x, b), fmaxf(a.y, b)); }
+DPH_HD float v_min3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
+DPH_HD f2 v_min3(f2 a, f2 b, f2 c) { return f2(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y))); }
+// |a| <= thr ? x : y
+DPH_HD float v_sel_small(float a, float thr, float x, float y) { return fabsf(a) <= thr ? x : y; }
+DPH_HD f2 v_sel_small(f2 a, float thr, f2 x, f2 y) { return f2(fabsf(a.x) <= thr ? x.x : y.x, fabsf(a.y) <= thr ? x.y : y.y); }
+DPH_HD float v_pick(bool c, float x, float y) { return c ? x : y; }
+DPH_HD f2 v_pick(bool c, f2 x, f2 y) { return f2(c ? x.x : y.x, c ? x.y : y.y); }
+DPH_HD float v_hsum(float a) { return a; }
+DPH_HD float v_hsum(f2 a) { return a.x + a.y; }
+DPH_HD float v_hmin(float a) { return a; }
+DPH_HD float v_hmin(f2 a) { return fminf(a.x, a.y); }
+
 // log1p(u): Taylor series of degree 6 for |u| <= 1/32 (truncation < 2e-10 relative), lg2-based beyond
 // (absolute error ~2e-7 there, on steps that change the model by more than 3%).
 constexpr float kLog1pSmall = 0.03125f;
-DPH_HD float log1p_acc(float u) {
-    float p = -1.0f / 6.0f;
-    p = f_fma(p, u, 0.2f);
-    p = f_fma(p, u, -0.25f);
-    p = f_fma(p, u, 1.0f / 3.0f);
-    p = f_fma(p, u, -0.5f);
+template <class T>
+DPH_HD T log1p_acc(T u) {
+    T p = T(-1.0f / 6.0f);
+    p = f_fma(p, u, T(0.2f));
+    p = f_fma(p, u, T(-0.25f));
+    p = f_fma(p, u, T(1.0f / 3.0f));
+    p = f_fma(p, u, T(-0.5f));
     p = f_fma(p * u, u, u);
-    float big = kLn2 * f_lg2(fmaxf(1.0f + u, 1e-37f));
-    return fabsf(u) <= kLog1pSmall ? p : big;
+    T big = v_lg2(v_max(u + T(1.0f), 1e-37f)) * T(kLn2);
+    return v_sel_small(u, kLog1pSmall, p, big);
 }
 
 // expm1(a) for |a| <= 1/16 (Taylor, degree 5, truncation < 2e-9 relative); callers handle larger |a| by
 // direct differences of the stored exponentials.
-DPH_HD float expm1_small(float a) {
-    float p = 1.0f / 120.0f;
-    p = f_fma(p, a, 1.0f / 24.0f);
-    p = f_fma(p, a, 1.0f / 6.0f);
-    p = f_fma(p, a, 0.5f);
+template <class T>
+DPH_HD T expm1_small(T a) {
+    T p = T(1.0f / 120.0f);
+    p = f_fma(p, a, T(1.0f / 24.0f));
+    p = f_fma(p, a, T(1.0f / 6.0f));
+    p = f_fma(p, a, T(0.5f));
     return f_fma(p * a, a, a);
 }
 constexpr float kSmallArg = 0.0625f;
@@ -165,25 +215,26 @@ DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
 
 struct Gauss2D {  // amp, x0, y0, sigma, offset
     static constexpr int P = 5, NE = 1;
-    struct Par { float amp, x0, y0, sig, off, s2, s3, nh; };
+    struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3; };
     struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
-    struct Geo { float dx, dy, r2; };
-    struct Diff { float dot, dr2, r20; };
+    template <class T> struct Geo { T dx, dy, r2; };
+    template <class T> struct Diff { T dot, dr2, r20; };
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
         float is = f_rcp(q.sig);
         q.s2 = is * is;
         q.s3 = q.s2 * is;
         q.nh = -0.5f * kLog2e * q.s2;
+        q.as2 = q.amp * q.s2; q.as3 = q.amp * q.s3;
     }
-    DPH_HD static void geometry(const Par& q, float cx, float cy, Geo& g) {
-        g.dx = cx - q.x0; g.dy = cy - q.y0; g.r2 = f_fma(g.dx, g.dx, g.dy * g.dy);
+    template <class T> DPH_HD static void geometry(const Par& q, T cx, T cy, Geo<T>& g) {
+        g.dx = cx - T(q.x0); g.dy = cy - T(q.y0); g.r2 = f_fma(g.dx, g.dx, g.dy * g.dy);
     }
-    DPH_HD static void expo(const Par& q, const Geo& g, float* e) { e[0] = f_ex2(q.nh * g.r2); }
-    DPH_HD static float value(const Par& q, const float* e) { return f_fma(q.amp, e[0], q.off); }
-    DPH_HD static void jac(const Par& q, const Geo& g, const float* e, float* J) {
-        float t = q.amp * e[0] * q.s2;
-        J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = q.amp * e[0] * q.s3 * g.r2; J[4] = 1.0f;
+    template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) { e[0] = v_ex2(g.r2 * T(q.nh)); }
+    template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
+    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
+        T t = e[0] * T(q.as2);
+        J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = e[0] * T(q.as3) * g.r2; J[4] = T(1.0f);
     }
     DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
         s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d4 = d[4];
@@ -194,28 +245,28 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
         s.k0 = f_fma(-s.c2, s.ndd, d[0]);                                 // d0 + c2 (d1^2 + d2^2)
     }
     // per-pixel step quantities, from the geometry at the NEW point (dx_old = dx_new + d1, ...)
-    DPH_HD static void diff(const Par&, const Step& s, const Geo& g1, Diff& df) {
-        df.dot = f_fma(g1.dx, s.d1, g1.dy * s.d2);
-        df.dr2 = f_fma(-2.0f, df.dot, s.ndd);       // r2_new - r2_old
-        df.r20 = g1.r2 - df.dr2;                    // r2_old
+    template <class T> DPH_HD static void diff(const Par&, const Step& s, const Geo<T>& g1, Diff<T>& df) {
+        df.dot = f_fma(g1.dx, T(s.d1), g1.dy * T(s.d2));
+        df.dr2 = f_fma(T(-2.0f), df.dot, T(s.ndd));  // r2_new - r2_old
+        df.r20 = g1.r2 - df.dr2;                     // r2_old
     }
-    DPH_HD static float delta(const Par& a, const Step& s, const Diff& df, const float* ea, const float* eb) {
-        float darg = f_fma(df.dr2, s.nh1, df.r20 * s.nds);
-        float de = fabsf(darg) <= kSmallArg ? ea[0] * expm1_small(darg) : eb[0] - ea[0];
-        return f_fma(s.d0, eb[0], f_fma(a.amp, de, s.d4));
+    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
+        T darg = f_fma(df.dr2, T(s.nh1), df.r20 * T(s.nds));
+        T de = v_sel_small(darg, kSmallArg, ea[0] * expm1_small(darg), eb[0] - ea[0]);
+        return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d4)));
     }
-    DPH_HD static float jdx(const Par&, const Step& s, const Diff& df, const float* ea) {
-        float lin = f_fma(s.c2, df.dot, f_fma(s.c3, df.r20, s.k0));
-        return f_fma(ea[0], lin, s.d4);
+    template <class T> DPH_HD static T jdx(const Par&, const Step& s, const Diff<T>& df, const T* ea) {
+        T lin = f_fma(T(s.c2), df.dot, f_fma(T(s.c3), df.r20, T(s.k0)));
+        return f_fma(ea[0], lin, T(s.d4));
     }
 };
 
 struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     static constexpr int P = 7, NE = 1;
     struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy; };
-    struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day; };
-    struct Geo { float dx, dy, u, v; };
-    struct Diff { float dx, dy, u, v; };
+    struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day, t1, t2; };
+    template <class T> struct Geo { T dx, dy, u, v; };
+    template <class T> struct Diff { T dx, dy, u, v; };
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];
 #if defined(__CUDA_ARCH__)
@@ -226,25 +277,25 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         q.isx = f_rcp(q.sx); q.isy = f_rcp(q.sy);
         q.ax = q.isx * q.isx; q.ay = q.isy * q.isy;
     }
-    DPH_HD static void geometry(const Par& q, float cx, float cy, Geo& g) {
-        g.dx = cx - q.x0; g.dy = cy - q.y0;
-        g.u = f_fma(q.c, g.dx, q.s * g.dy);
-        g.v = f_fma(q.c, g.dy, -q.s * g.dx);
+    template <class T> DPH_HD static void geometry(const Par& q, T cx, T cy, Geo<T>& g) {
+        g.dx = cx - T(q.x0); g.dy = cy - T(q.y0);
+        g.u = f_fma(T(q.c), g.dx, g.dy * T(q.s));
+        g.v = f_fma(T(q.c), g.dy, g.dx * T(-q.s));
     }
-    DPH_HD static void expo(const Par& q, const Geo& g, float* e) {
-        e[0] = f_ex2(-0.5f * kLog2e * f_fma(g.u * g.u, q.ax, g.v * g.v * q.ay));
+    template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) {
+        e[0] = v_ex2(f_fma(g.u * g.u, T(q.ax), g.v * g.v * T(q.ay)) * T(-0.5f * kLog2e));
     }
-    DPH_HD static float value(const Par& q, const float* e) { return f_fma(q.amp, e[0], q.off); }
-    DPH_HD static void jac(const Par& q, const Geo& g, const float* e, float* J) {
-        float ae = q.amp * e[0];
-        float uax = g.u * q.ax, vay = g.v * q.ay;
+    template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
+    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
+        T ae = e[0] * T(q.amp);
+        T uax = g.u * T(q.ax), vay = g.v * T(q.ay);
         J[0] = e[0];
-        J[1] = ae * f_fma(uax, q.c, -vay * q.s);
-        J[2] = ae * f_fma(uax, q.s, vay * q.c);
-        J[3] = ae * g.u * uax * q.isx;
-        J[4] = ae * g.v * vay * q.isy;
-        J[5] = ae * g.u * g.v * (q.ay - q.ax);
-        J[6] = 1.0f;
+        J[1] = ae * f_fma(uax, T(q.c), vay * T(-q.s));
+        J[2] = ae * f_fma(uax, T(q.s), vay * T(q.c));
+        J[3] = ae * g.u * uax * T(q.isx);
+        J[4] = ae * g.v * vay * T(q.isy);
+        J[5] = ae * g.u * g.v * T(q.ay - q.ax);
+        J[6] = T(1.0f);
     }
     DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
         s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3]; s.d4 = d[4]; s.d5 = d[5]; s.d6 = d[6];
@@ -263,32 +314,33 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         s.axb = b.ax; s.ayb = b.ay;
         s.dax = -d[3] * (2.0f * a.sx + d[3]) * a.ax * b.ax;
         s.day = -d[4] * (2.0f * a.sy + d[4]) * a.ay * b.ay;
+        s.t1 = -f_fma(s.cb, s.d1, s.sb * s.d2);   // rotation of the centre shift, new frame
+        s.t2 = -f_fma(s.cb, s.d2, -s.sb * s.d1);
     }
-    DPH_HD static void diff(const Par& a, const Step& s, const Geo& g1, Diff& df) {
-        df.dx = g1.dx + s.d1; df.dy = g1.dy + s.d2;  // offsets from the OLD centre
-        df.u = f_fma(a.c, df.dx, a.s * df.dy);
-        df.v = f_fma(a.c, df.dy, -a.s * df.dx);
+    template <class T> DPH_HD static void diff(const Par& a, const Step& s, const Geo<T>& g1, Diff<T>& df) {
+        df.dx = g1.dx + T(s.d1); df.dy = g1.dy + T(s.d2);  // offsets from the OLD centre
+        df.u = f_fma(T(a.c), df.dx, df.dy * T(a.s));
+        df.v = f_fma(T(a.c), df.dy, df.dx * T(-a.s));
     }
-    DPH_HD static float delta(const Par& a, const Step& s, const Diff& ga, const float* ea, const float* eb) {
-        float du = f_fma(s.dc, ga.dx, s.dsn * ga.dy) - f_fma(s.cb, s.d1, s.sb * s.d2);
-        float dv = f_fma(s.dc, ga.dy, -s.dsn * ga.dx) - f_fma(s.cb, s.d2, -s.sb * s.d1);
-        float du2 = du * f_fma(2.0f, ga.u, du);
-        float dv2 = dv * f_fma(2.0f, ga.v, dv);
-        float t = f_fma(du2, s.axb, ga.u * ga.u * s.dax) + f_fma(dv2, s.ayb, ga.v * ga.v * s.day);
-        float darg = -0.5f * t;
-        float de = fabsf(darg) <= kSmallArg ? ea[0] * expm1_small(darg) : eb[0] - ea[0];
-        return f_fma(s.d0, eb[0], f_fma(a.amp, de, s.d6));
+    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& ga, const T* ea, const T* eb) {
+        T du = f_fma(T(s.dc), ga.dx, f_fma(T(s.dsn), ga.dy, T(s.t1)));
+        T dv = f_fma(T(s.dc), ga.dy, f_fma(T(-s.dsn), ga.dx, T(s.t2)));
+        T du2 = du * f_fma(T(2.0f), ga.u, du);
+        T dv2 = dv * f_fma(T(2.0f), ga.v, dv);
+        T t = f_fma(du2, T(s.axb), ga.u * ga.u * T(s.dax)) + f_fma(dv2, T(s.ayb), ga.v * ga.v * T(s.day));
+        T darg = t * T(-0.5f);
+        T de = v_sel_small(darg, kSmallArg, ea[0] * expm1_small(darg), eb[0] - ea[0]);
+        return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d6)));
     }
-    DPH_HD static float jdx(const Par& a, const Step& s, const Diff& ga, const float* ea) {
-        float ae = a.amp * ea[0];
-        float uax = ga.u * a.ax, vay = ga.v * a.ay;
-        float r = s.d6;
-        r = f_fma(ea[0], s.d0, r);
-        r = f_fma(ae * f_fma(uax, a.c, -vay * a.s), s.d1, r);
-        r = f_fma(ae * f_fma(uax, a.s, vay * a.c), s.d2, r);
-        r = f_fma(ae * ga.u * uax * a.isx, s.d3, r);
-        r = f_fma(ae * ga.v * vay * a.isy, s.d4, r);
-        r = f_fma(ae * ga.u * ga.v * (a.ay - a.ax), s.d5, r);
+    template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& ga, const T* ea) {
+        T ae = ea[0] * T(a.amp);
+        T uax = ga.u * T(a.ax), vay = ga.v * T(a.ay);
+        T r = f_fma(ea[0], T(s.d0), T(s.d6));
+        r = f_fma(ae * f_fma(uax, T(a.c), vay * T(-a.s)), T(s.d1), r);
+        r = f_fma(ae * f_fma(uax, T(a.s), vay * T(a.c)), T(s.d2), r);
+        r = f_fma(ae * ga.u * uax, T(a.isx * s.d3), r);
+        r = f_fma(ae * ga.v * vay, T(a.isy * s.d4), r);
+        r = f_fma(ae * ga.u * ga.v, T((a.ay - a.ax) * s.d5), r);
         return r;
     }
 };
@@ -299,49 +351,49 @@ struct MultiExp {
     static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = NEXP;
     struct Par { float a[NEXP], k[NEXP], off; };
     struct Step { float da[NEXP], dk[NEXP], doff; };
-    struct Geo { float x; };
-    struct Diff { float x; };
+    template <class T> struct Geo { T x; };
+    template <class T> struct Diff { T x; };
     DPH_HD static void prepare(const float* p, Par& q) {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) { q.a[i] = p[2 * i]; q.k[i] = p[2 * i + 1]; }
         q.off = OFFSET ? p[2 * NEXP] : 0.0f;
     }
-    DPH_HD static void geometry(const Par&, float cx, float, Geo& g) { g.x = cx; }
-    DPH_HD static void expo(const Par& q, const Geo& g, float* e) {
+    template <class T> DPH_HD static void geometry(const Par&, T cx, T, Geo<T>& g) { g.x = cx; }
+    template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) {
 #pragma unroll
-        for (int i = 0; i < NEXP; ++i) e[i] = f_ex2(-kLog2e * q.k[i] * g.x);
+        for (int i = 0; i < NEXP; ++i) e[i] = v_ex2(g.x * T(-kLog2e * q.k[i]));
     }
-    DPH_HD static float value(const Par& q, const float* e) {
-        float f = q.off;
+    template <class T> DPH_HD static T value(const Par& q, const T* e) {
+        T f = T(q.off);
 #pragma unroll
-        for (int i = 0; i < NEXP; ++i) f = f_fma(q.a[i], e[i], f);
+        for (int i = 0; i < NEXP; ++i) f = f_fma(T(q.a[i]), e[i], f);
         return f;
     }
-    DPH_HD static void jac(const Par& q, const Geo& g, const float* e, float* J) {
+    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
 #pragma unroll
-        for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[i]; J[2 * i + 1] = -q.a[i] * g.x * e[i]; }
-        if (OFFSET) J[2 * NEXP] = 1.0f;
+        for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[i]; J[2 * i + 1] = g.x * e[i] * T(-q.a[i]); }
+        if (OFFSET) J[2 * NEXP] = T(1.0f);
     }
     DPH_HD static void prepare_step(const Par&, const Par&, const float* d, Step& s) {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) { s.da[i] = d[2 * i]; s.dk[i] = d[2 * i + 1]; }
         s.doff = OFFSET ? d[2 * NEXP] : 0.0f;
     }
-    DPH_HD static void diff(const Par&, const Step&, const Geo& g1, Diff& df) { df.x = g1.x; }
-    DPH_HD static float delta(const Par& a, const Step& s, const Diff& ga, const float* ea, const float* eb) {
-        float r = s.doff;
+    template <class T> DPH_HD static void diff(const Par&, const Step&, const Geo<T>& g1, Diff<T>& df) { df.x = g1.x; }
+    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& ga, const T* ea, const T* eb) {
+        T r = T(s.doff);
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) {
-            float darg = -s.dk[i] * ga.x;
-            float de = fabsf(darg) <= kSmallArg ? ea[i] * expm1_small(darg) : eb[i] - ea[i];
-            r = f_fma(s.da[i], eb[i], f_fma(a.a[i], de, r));
+            T darg = ga.x * T(-s.dk[i]);
+            T de = v_sel_small(darg, kSmallArg, ea[i] * expm1_small(darg), eb[i] - ea[i]);
+            r = f_fma(T(s.da[i]), eb[i], f_fma(T(a.a[i]), de, r));
         }
         return r;
     }
-    DPH_HD static float jdx(const Par& a, const Step& s, const Diff& ga, const float* ea) {
-        float r = s.doff;
+    template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& ga, const T* ea) {
+        T r = T(s.doff);
 #pragma unroll
-        for (int i = 0; i < NEXP; ++i) r = f_fma(ea[i], f_fma(-a.a[i] * ga.x, s.dk[i], s.da[i]), r);
+        for (int i = 0; i < NEXP; ++i) r = f_fma(ea[i], f_fma(ga.x, T(-a.a[i] * s.dk[i]), T(s.da[i])), r);
         return r;
     }
 };
@@ -350,14 +402,15 @@ struct MultiExp {
 // Per-fit pixel state, pointer based so that the device (shared memory) and host builds share code.
 //   y[M]               data (MLE: already clamped to >= 0)
 //   e[2][NE][stride]   stored exponentials, double buffered: `cur` is the accepted point, 1-cur the trial
-//   cxy[M]             pixel coordinates (x, y), shared by all fits
-struct Coord { float x, y; };
+//   cx[M], cy[M]       pixel coordinates, shared by all fits (cy unused by 1-D models)
+// All arrays are 8-byte aligned and indexed by pixel, so that a pair of adjacent pixels is one 64-bit access.
 
 template <int NE>
 struct PixelState {
     float* y;
     float* e;  // [2][NE][stride]
-    const Coord* cxy;
+    const float* cx;
+    const float* cy;
     int M, stride;
     int cur;
     DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * stride; }
@@ -421,22 +474,38 @@ struct Normal {  // per-lane partial sums of one pass, group totals after the re
     }
 };
 
-template <int P>
-DPH_HD void accumulate(Normal<P>& n, const float* J, float w, float res) {
+// partial sums of one lane while it walks its pixels; T = f2 for pixel pairs, float for single pixels
+template <int P, class T>
+struct Acc {
+    T A[NT<P>::value];
+    T g[P];
+    T actual, predicted, chi1;
+    T lo;  // smallest model value met (regular case: stays > 0)
+    DPH_HD void clear() {
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-        float wj = w * J[i];
+        for (int i = 0; i < NT<P>::value; ++i) A[i] = T(0.0f);
 #pragma unroll
-        for (int j = i; j < P; ++j) n.A[tri<P>(i, j)] = f_fma(wj, J[j], n.A[tri<P>(i, j)]);
-        n.g[i] = f_fma(J[i], res, n.g[i]);
+        for (int i = 0; i < P; ++i) g[i] = T(0.0f);
+        actual = predicted = chi1 = T(0.0f);
+        lo = T(1.0f);
     }
-}
+    DPH_HD void add(const T* J, T w, T res) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            T wj = w * J[i];
+#pragma unroll
+            for (int j = i; j < P; ++j) A[tri<P>(i, j)] = f_fma(wj, J[j], A[tri<P>(i, j)]);
+            g[i] = f_fma(J[i], res, g[i]);
+        }
+    }
+};
 
 // Poisson term  t(f) = f - y ln(f / y)  with the reference's zeroing rule (lm.py:70-78); slow path.
 DPH_HD float mle_term_direct(float f, float y) {
     float l = (y > 0.0f && f > 0.0f) ? y * kLn2 * (f_lg2(f) - f_lg2(y)) : 0.0f;
     return f - l;
 }
+DPH_HD f2 mle_term_direct(f2 f, f2 y) { return f2(mle_term_direct(f.x, y.x), mle_term_direct(f.y, y.y)); }
 DPH_HD float clamp_nonneg(float f) { return f <= 0.0f ? 0.0f : f; }  // lm.py:117
 
 // MLE weights at a model value f (already clamped): w = y/f^2, res = 1 - y/f; invalid -> (0, 1)  (lm.py:86-102)
@@ -449,102 +518,173 @@ DPH_HD void mle_weights(float f, float y, float& w, float& res) {
     res = ok ? 1.0f - yf : 1.0f;
 }
 
-// Evaluation at the trial point q1 = q0 + d.  Reads the exponentials of the accepted point (buffer
-// cur), writes the trial ones (buffer 1-cur), accumulates the chi-square reductions from per-pixel
-// differences and, speculatively, A and g at the trial point.  QUIRK (lm.py:446-449): the predicted
-// model is f(x_new) + J(x_old) d.  With `init` the accepted point does not exist yet: the pass is run
-// with d = 0 and the old exponentials are taken equal to the new ones (actual = predicted = 0).
+// One pixel (T = float) or one pair of adjacent pixels (T = f2) of the regular, branch-free trial
+// evaluation: model at the trial point q1 = q0 + d, the chi-square reductions from per-pixel differences
+// and, speculatively, the normal equations at the trial point.  QUIRK (lm.py:446-449): the predicted
+// model is f(x_new) + J(x_old) d.
+template <class Mo, bool MLE, bool PRED, class T>
+DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1, const typename Mo::Step& st, bool init,
+                          bool want_chi, T cx, T cy, T y, const T* e0in, T* e1, Acc<Mo::P, T>& n) {
+    constexpr int P = Mo::P, NE = Mo::NE;
+    typename Mo::template Geo<T> g1;
+    typename Mo::template Diff<T> df;
+    T e0[NE], J[P];
+    Mo::geometry(q1, cx, cy, g1);
+    Mo::expo(q1, g1, e1);
+#pragma unroll
+    for (int j = 0; j < NE; ++j) e0[j] = v_pick(init, e1[j], e0in[j]);
+    Mo::diff(q0, st, g1, df);
+    const T f0 = Mo::value(q0, e0);
+    const T f1 = Mo::value(q1, e1);
+    const T dl = Mo::delta(q0, st, df, e0, e1);
+    Mo::jac(q1, g1, e1, J);
+    if (MLE) {
+        const T f1c = v_max(f1, 0.0f);
+        const T rf0 = v_rcp(v_max(f0, 0.0f));
+        n.actual = f_fma(y, log1p_acc(dl * rf0), n.actual) - dl;
+        if (PRED) {
+            const T jd = Mo::jdx(q0, st, df, e0);
+            const T dp = dl + jd;
+            n.lo = v_min3(n.lo, f1c, f1c + jd);  // f_old was a trial value itself and was checked then
+            n.predicted = f_fma(y, log1p_acc(dp * rf0), n.predicted) - dp;
+        } else {
+            n.lo = v_min3(n.lo, f1c, f1c);
+        }
+        const T rf1 = v_rcp(f1c);
+        const T yf = y * rf1;
+        n.add(J, yf * rf1, T(1.0f) - yf);
+        if (want_chi) n.chi1 = n.chi1 + (mle_term_direct(f1c, y) - y);
+    } else {
+        const T r0 = f0 - y, r1 = f1 - y;
+        n.actual = n.actual - dl * f_fma(T(0.5f), dl, r0);
+        if (PRED) {
+            const T dp = dl + Mo::jdx(q0, st, df, e0);
+            n.predicted = n.predicted - dp * f_fma(T(0.5f), dp, r0);
+        }
+        n.chi1 = f_fma(r1 * T(0.5f), r1, n.chi1);
+        n.add(J, T(1.0f), r1);
+    }
+}
+
+// Evaluation at the trial point for all pixels of the fit owned by this lane group.  Reads the exponentials
+// of the accepted point (buffer cur), writes the trial ones (buffer 1-cur).  With `init` the accepted point
+// does not exist yet: the pass is run with d = 0 and the old exponentials are taken equal to the new ones
+// (actual = predicted = 0).
 //
-// FAST is the branch-free version for the regular case (all model values > 0, finite); a group that
-// meets anything else raises kFlagIrregular and the caller repeats the pass with FAST = false, which
-// implements the reference's clamps and zeroing rules literally.
+// FAST walks pairs of adjacent pixels with packed f32x2 arithmetic (pixel_regular<f2>) and treats only the
+// regular case (all model values > 0, finite); a group that meets anything else raises kFlagIrregular and
+// the caller repeats the pass with FAST = false, which implements the reference's clamps and zeroing rules
+// literally, pixel by pixel.
 template <class Mo, bool MLE, bool PRED, bool FAST, int G>
 DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const typename Mo::Par& q0,
                        const typename Mo::Par& q1, const typename Mo::Step& st, bool init, bool want_chi,
                        Normal<Mo::P>& n) {
     constexpr int P = Mo::P, NE = Mo::NE;
-    n.clear();
-    // running pointers (one element per lane and trip)
-    const float* e0p = px.ebuf(px.cur, 0) + ln.lane;
-    float* e1p = px.ebuf(1 - px.cur, 0) + ln.lane;
-    const float* yp = px.y + ln.lane;
-    const Coord* cp = px.cxy + ln.lane;
+    const float* e0b = px.ebuf(px.cur, 0);
+    float* e1b = px.ebuf(1 - px.cur, 0);
     const int stride = px.stride;
-    float lo = 1.0f;  // smallest model value met (regular case: stays > 0)
+    n.clear();
+    if (FAST) {
+        Acc<P, f2> a2;
+        a2.clear();
+        const int npair = px.M >> 1;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 2
+#pragma unroll 1
 #endif
-    for (int i = ln.lane; i < px.M; i += G, e0p += G, e1p += G, yp += G, cp += G) {
-        typename Mo::Geo g1;
-        typename Mo::Diff df;
-        float e0[NE], e1[NE], J[P];
-        const Coord c = *cp;
-        Mo::geometry(q1, c.x, c.y, g1);
-        Mo::expo(q1, g1, e1);
+        for (int q = ln.lane; q < npair; q += G) {
+            const int i = 2 * q;
+            f2 e0[NE], e1[NE];
 #pragma unroll
-        for (int j = 0; j < NE; ++j) {
-            float t = e0p[j * stride];
-            e0[j] = init ? e1[j] : t;
-            e1p[j * stride] = e1[j];
+            for (int j = 0; j < NE; ++j) e0[j] = *reinterpret_cast<const f2*>(e0b + j * stride + i);
+            const f2 cx = *reinterpret_cast<const f2*>(px.cx + i);
+            const f2 cy = *reinterpret_cast<const f2*>(px.cy + i);
+            const f2 y = *reinterpret_cast<const f2*>(px.y + i);
+            pixel_regular<Mo, MLE, PRED, f2>(q0, q1, st, init, want_chi, cx, cy, y, e0, e1, a2);
+#pragma unroll
+            for (int j = 0; j < NE; ++j) *reinterpret_cast<f2*>(e1b + j * stride + i) = e1[j];
         }
-        const float y = *yp;
-        Mo::diff(q0, st, g1, df);
-        const float f0 = Mo::value(q0, e0);
-        const float f1 = Mo::value(q1, e1);
-        const float dl = Mo::delta(q0, st, df, e0, e1);
-        Mo::jac(q1, g1, e1, J);
-        if (MLE) {
-            if (FAST) {
-                const float f0c = fmaxf(f0, 0.0f), f1c = fmaxf(f1, 0.0f);
-                const float rf0 = f_rcp(f0c);
-                n.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
-                if (PRED) {
-                    const float jd = Mo::jdx(q0, st, df, e0);
-                    const float dp = dl + jd;
-                    lo = fminf(lo, fminf(f0c, fminf(f1c, f1c + jd)));
-                    n.predicted += f_fma(y, log1p_acc(dp * rf0), -dp);
-                } else {
-                    lo = fminf(lo, fminf(f0c, f1c));
-                }
-                const float rf1 = f_rcp(f1c);
-                const float yf = y * rf1;
-                accumulate<P>(n, J, yf * rf1, 1.0f - yf);
-                if (want_chi) n.chi1 += mle_term_direct(f1c, y) - y;
-            } else {
-                if (!f_finite(f1)) n.flags |= kFlagNonFinite;
+        Acc<P, float> a1;
+#pragma unroll
+        for (int k = 0; k < NT<P>::value; ++k) a1.A[k] = v_hsum(a2.A[k]);
+#pragma unroll
+        for (int k = 0; k < P; ++k) a1.g[k] = v_hsum(a2.g[k]);
+        a1.actual = v_hsum(a2.actual); a1.predicted = v_hsum(a2.predicted); a1.chi1 = v_hsum(a2.chi1);
+        a1.lo = v_hmin(a2.lo);
+        if ((px.M & 1) && ln.lane == npair % G) {  // odd pixel count: the last pixel alone
+            const int i = px.M - 1;
+            float e0[NE], e1[NE];
+#pragma unroll
+            for (int j = 0; j < NE; ++j) e0[j] = e0b[j * stride + i];
+            pixel_regular<Mo, MLE, PRED, float>(q0, q1, st, init, want_chi, px.cx[i], px.cy[i], px.y[i], e0, e1, a1);
+#pragma unroll
+            for (int j = 0; j < NE; ++j) e1b[j * stride + i] = e1[j];
+        }
+#pragma unroll
+        for (int k = 0; k < NT<P>::value; ++k) n.A[k] = a1.A[k];
+#pragma unroll
+        for (int k = 0; k < P; ++k) n.g[k] = a1.g[k];
+        n.actual = a1.actual; n.predicted = a1.predicted; n.chi1 = a1.chi1;
+        if (MLE && !(a1.lo > 0.0f)) n.flags |= kFlagIrregular;  // also catches NaN
+    } else {
+        Acc<P, float> a1;
+        a1.clear();
+        for (int i = ln.lane; i < px.M; i += G) {
+            typename Mo::template Geo<float> g1;
+            typename Mo::template Diff<float> df;
+            float e0[NE], e1[NE], J[P];
+            Mo::geometry(q1, px.cx[i], px.cy[i], g1);
+            Mo::expo(q1, g1, e1);
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+                float t = e0b[j * stride + i];
+                e0[j] = init ? e1[j] : t;
+                e1b[j * stride + i] = e1[j];
+            }
+            const float y = px.y[i];
+            Mo::diff(q0, st, g1, df);
+            const float f0 = Mo::value(q0, e0);
+            const float f1 = Mo::value(q1, e1);
+            const float dl = Mo::delta(q0, st, df, e0, e1);
+            Mo::jac(q1, g1, e1, J);
+            if (!f_finite(f1)) n.flags |= kFlagNonFinite;
+            if (MLE) {
                 const float f0c = clamp_nonneg(f0), f1c = clamp_nonneg(f1);
                 const float rf0 = f_rcp(f0c);
                 const bool reg = (f0c > 0.0f) && (f1c > 0.0f);
-                if (reg) n.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
-                else n.actual += mle_term_direct(f0c, y) - mle_term_direct(f1c, y);
+                if (reg) a1.actual += f_fma(y, log1p_acc(dl * rf0), -dl);
+                else a1.actual += mle_term_direct(f0c, y) - mle_term_direct(f1c, y);
                 if (PRED) {
                     const float jd = Mo::jdx(q0, st, df, e0);
                     const float fp = f1c + jd;
                     if (fp < 0.0f) n.flags |= kFlagPredNeg;
                     if (reg && fp > 0.0f) {
                         const float dp = dl + jd;
-                        n.predicted += f_fma(y, log1p_acc(dp * rf0), -dp);
+                        a1.predicted += f_fma(y, log1p_acc(dp * rf0), -dp);
                     } else {
-                        n.predicted += mle_term_direct(f0c, y) - mle_term_direct(fp, y);
+                        a1.predicted += mle_term_direct(f0c, y) - mle_term_direct(fp, y);
                     }
                 }
                 float w, res;
                 mle_weights(f1c, y, w, res);
-                accumulate<P>(n, J, w, res);
-                if (want_chi) n.chi1 += mle_term_direct(f1c, y) - y;
+                a1.add(J, w, res);
+                if (want_chi) a1.chi1 += mle_term_direct(f1c, y) - y;
+            } else {
+                const float r0 = f0 - y, r1 = f1 - y;
+                a1.actual = f_fma(-dl, f_fma(0.5f, dl, r0), a1.actual);
+                if (PRED) {
+                    const float dp = dl + Mo::jdx(q0, st, df, e0);
+                    a1.predicted = f_fma(-dp, f_fma(0.5f, dp, r0), a1.predicted);
+                }
+                a1.chi1 = f_fma(0.5f * r1, r1, a1.chi1);
+                a1.add(J, 1.0f, r1);
             }
-        } else {
-            const float r0 = f0 - y, r1 = f1 - y;
-            n.actual = f_fma(-dl, f_fma(0.5f, dl, r0), n.actual);
-            if (PRED) {
-                const float dp = dl + Mo::jdx(q0, st, df, e0);
-                n.predicted = f_fma(-dp, f_fma(0.5f, dp, r0), n.predicted);
-            }
-            n.chi1 = f_fma(0.5f * r1, r1, n.chi1);
-            accumulate<P>(n, J, 1.0f, r1);
         }
+#pragma unroll
+        for (int k = 0; k < NT<P>::value; ++k) n.A[k] = a1.A[k];
+#pragma unroll
+        for (int k = 0; k < P; ++k) n.g[k] = a1.g[k];
+        n.actual = a1.actual; n.predicted = a1.predicted; n.chi1 = a1.chi1;
     }
-    if (MLE && FAST && !(lo > 0.0f)) n.flags |= kFlagIrregular;  // also catches NaN
     n.reduce(ln);
     if (!MLE && !f_finite(n.chi1)) n.flags |= kFlagNonFinite;
 }

@@ -266,12 +266,13 @@ __global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(cons
     constexpr int FPW = 32 / G;  // fits in flight per warp
     const int M = a.h * a.w;
     const int stride = padded_stride(M, G);
-    Coord* cxy = reinterpret_cast<Coord*>(smem);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
-        Coord c;
-        if (a.xaxis) { c.x = a.xaxis[i]; c.y = 0.0f; }
-        else { c.x = float(i % a.w); c.y = float(i / a.w); }
-        cxy[i] = c;
+    const int Mp = (M + 1) & ~1;
+    float* cx = smem;
+    float* cy = smem + Mp;
+    for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
+        const int k = i < M ? i : M - 1;
+        cx[i] = a.xaxis ? a.xaxis[k] : float(k % a.w);
+        cy[i] = a.xaxis ? 0.0f : float(k / a.w);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(cons
     const int region = group_region(stride, Mo::NE);
     float* base = smem + 2 * ((M + 1) & ~1) + (warp * FPW + grp) * region;
     Lanes<G> ln{lane % G, G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G))};
-    PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cxy, M, stride, 0};
+    PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cx, cy, M, stride, 0};
     IO io{a, base + stride + kStageExtra};
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
 }

@@ -119,14 +119,19 @@ struct HostIoMain {
 template <class Mo, bool MLE>
 static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b) {
     const int M = h * w;
-    std::vector<Coord> cxy(M);
+    const int stride = (M + 1) & ~1;  // even: pairs of adjacent pixels are 8-byte aligned
+    std::vector<double> backing(4 * stride);  // double: 8-byte aligned storage
+    float* cx = reinterpret_cast<float*>(backing.data());
+    float* cy = cx + stride;
     for (int i = 0; i < M; ++i) {
-        if (xaxis) { cxy[i].x = xaxis[i]; cxy[i].y = 0.f; }
-        else { cxy[i].x = float(i % w); cxy[i].y = float(i / w); }
+        if (xaxis) { cx[i] = xaxis[i]; cy[i] = 0.f; }
+        else { cx[i] = float(i % w); cy[i] = float(i / w); }
     }
-    std::vector<float> y(M), e(2 * Mo::NE * M);
+    std::vector<double> ybuf(stride), ebuf(Mo::NE * stride);
+    float* y = reinterpret_cast<float*>(ybuf.data());
+    float* e = reinterpret_cast<float*>(ebuf.data());
     Lanes<1> ln{0, 1u};
-    PixelState<Mo::NE> px{y.data(), e.data(), cxy.data(), M, M, 0};
+    PixelState<Mo::NE> px{y, e, cx, cy, M, stride, 0};
     HostIoPrefit<Mo> ioa{b};
     run_stage<StageA<Mo>, Mo, 1>(ln, px, opt, ioa);
     b.parked.clear();
