@@ -70,6 +70,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
         self.active = False  # set around the timed regions: only those samples count
+        self.ready = threading.Event()  # NVML initialised (nvmlInit takes ~100 ms and must not land in a timed region)
 
     def run(self):
         try:
@@ -84,6 +85,7 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
             }
+            self.ready.set()
             while not self.stop_flag:
                 if self.active:
                     self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
@@ -92,6 +94,7 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.002)
         except Exception as e:  # NVML missing: report that, never fail the run
             self.reasons.add("nvml_unavailable:" + type(e).__name__)
+        self.ready.set()
 
     def summary(self):
         return {
@@ -159,13 +162,14 @@ def main():
     dev = torch.device("cuda", local)
     n = args.fits
 
+    sampler = ClockSampler(local)
+    sampler.start()
+
     # ---- synthetic inputs: N_SETS distinct batches per rank (seeded), resident in HBM
     sets = [synth.WORKLOADS[WORKLOAD](n, seed=1000 * rank + s) for s in range(N_SETS)]
     d_data = [torch.from_numpy(s["data"]).to(dev) for s in sets]
     d_p0 = [torch.from_numpy(s["p0"]).to(dev) for s in sets]
 
-    sampler = ClockSampler(local)
-    sampler.start()
 
     def step(i, counts=False):
         return dph.curve_fit_batch(models.gauss2d, d_data[i % N_SETS], d_p0[i % N_SETS], "mle", return_counts=counts,
@@ -176,6 +180,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler.ready.wait(timeout=30)
     for i in range(args.warmup):
         step(i)
     barrier()
