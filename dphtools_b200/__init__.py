@@ -1,7 +1,7 @@
 """B200-native batched Levenberg-Marquardt / Poisson-MLE fitter (drop-in for ``dphtools.utils.lm``)."""
 
 from . import models, synth  # noqa: F401
-from .lm import BatchResult, curve_fit, curve_fit_batch, pinned_empty  # noqa: F401
+from .lm import BatchResult, covariance, curve_fit, curve_fit_batch, pinned_empty  # noqa: F401
 from .models import gauss2d, gauss2d_elliptical, multi_exp  # noqa: F401
 
 __version__ = "0.1.0"

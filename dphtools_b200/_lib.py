@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("DPHLM_LIB") or os.path.join(os.path.dirname(os.path.a
 
 SYMBOLS = [
     "dphlm_desc_init", "dphlm_fit_batch", "dphlm_fit_batch_host", "dphlm_host_alloc", "dphlm_host_free",
-    "dphlm_device_count", "dphlm_version", "dphlm_last_error", "dphlm_last_kernel_ms",
+    "dphlm_device_count", "dphlm_version", "dphlm_last_error", "dphlm_last_kernel_ms", "dphlm_covariance",
 ]
 
 
@@ -48,6 +48,8 @@ def lib():
         L.dphlm_fit_batch.restype = ctypes.c_int
         L.dphlm_fit_batch_host.argtypes = [ctypes.POINTER(Desc), ctypes.c_int]
         L.dphlm_fit_batch_host.restype = ctypes.c_int
+        L.dphlm_covariance.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.dphlm_covariance.restype = ctypes.c_int
         L.dphlm_host_alloc.argtypes = [ctypes.c_size_t]
         L.dphlm_host_alloc.restype = ctypes.c_void_p
         L.dphlm_host_free.argtypes = [ctypes.c_void_p]

@@ -48,13 +48,10 @@ int auto_group(int M) {
     return 16;
 }
 
-int validate(const dphlm_desc* d) {
+int validate_shape(const dphlm_desc* d) {
     if (!d) return fail("null descriptor");
     if (d->n_fits < 0) return fail("n_fits < 0");
     if (d->dim0 < 1 || d->dim1 < 1) return fail("dim0/dim1 must be >= 1");
-    if (d->method != DPHLM_LS && d->method != DPHLM_MLE) return fail("Method not recognized");
-    if (d->n_fits > 0 && (!d->data || !d->p0 || !d->popt || !d->info || !d->nfev || !d->chisq))
-        return fail("null data/p0/popt/info/nfev/chisq pointer");
     switch (d->model) {
         case DPHLM_GAUSS2D:
             if (d->n_param != 5) return fail("gauss2d takes 5 parameters");
@@ -72,6 +69,16 @@ int validate(const dphlm_desc* d) {
     }
     if (d->n_param > d->dim0 * d->dim1) return fail("Improper input: N must not exceed M");
     return 0;
+}
+
+int validate(const dphlm_desc* d) {
+    if (!d) return fail("null descriptor");
+    if (d->n_fits < 0) return fail("n_fits < 0");
+    if (d->dim0 < 1 || d->dim1 < 1) return fail("dim0/dim1 must be >= 1");
+    if (d->method != DPHLM_LS && d->method != DPHLM_MLE) return fail("Method not recognized");
+    if (d->n_fits > 0 && (!d->data || !d->p0 || !d->popt || !d->info || !d->nfev || !d->chisq))
+        return fail("null data/p0/popt/info/nfev/chisq pointer");
+    return validate_shape(d);
 }
 
 // `ws` (optional): caller-provided device workspace of at least workspace_bytes(d)
@@ -250,6 +257,21 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     }
     cudaSetDevice(prev);
     return rc;
+}
+
+int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int kind, void* stream) {
+    if (validate_shape(d)) return -1;
+    if (kind != DPHLM_COV_JTJ && kind != DPHLM_COV_CRLB) return fail("kind must be DPHLM_COV_JTJ or DPHLM_COV_CRLB");
+    if (d->n_fits > 0 && (!popt || !pcov)) return fail("null popt/pcov pointer");
+    if (d->n_fits == 0) return 0;
+    CovArgs a{popt, d->xaxis, pcov, d->n_fits, d->dim0, d->dim1, kind};
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (d->model) {
+        case DPHLM_GAUSS2D: return launch_cov_gauss2d(a, s);
+        case DPHLM_GAUSS2D_ELLIPTICAL: return launch_cov_gauss2d_elliptical(a, s);
+        case DPHLM_MULTI_EXP: return launch_cov_multi_exp(d->n_param, a, s);
+    }
+    return fail("unknown model id");
 }
 
 void* dphlm_host_alloc(size_t bytes) {

@@ -286,6 +286,76 @@ __global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(cons
 }
 #endif
 
+// ------------------------------------------------------------------------------------ covariance
+// Per-fit parameter covariance from the Jacobian at `popt` (second return value of curve_fit):
+//   kind 0: pinv(J^T J) of the unweighted Jacobian, the reference's pcov (dphtools/utils/lm.py:672-677);
+//   kind 1: Poisson Cramer-Rao bound (J^T diag(1/f) J)^-1, the uncertainty an MLE user actually wants
+//           (precedent: notebooks/MLE_LevMarq_4Param_2013_11_12.m:145-168).
+// Eight lanes per fit, no shared memory; a rank-deficient matrix (the reference would drop singular values)
+// yields NaNs.
+struct CovArgs {
+    const float* popt;
+    const float* xaxis;
+    float* pcov;
+    long long n_fits;
+    int h, w, kind;
+};
+
+template <class Mo>
+__global__ void __launch_bounds__(128) dphlm_cov_kernel(const CovArgs a) {
+    constexpr int P = Mo::P, G = 8;
+    const int lane = threadIdx.x & 31;
+    const long long fit = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool active = fit < a.n_fits;
+    Lanes<G> ln{lane % G, 0xffu << ((lane / G) * G)};
+    float p[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) p[k] = active ? a.popt[fit * P + k] : 1.0f;
+    typename Mo::Par q;
+    Mo::prepare(p, q);
+    Acc<P, float> acc;
+    acc.clear();
+    const int M = a.h * a.w;
+    for (int i = ln.lane; i < M; i += G) {
+        typename Mo::template Geo<float> g;
+        float e[Mo::NE], J[P];
+        const float cx = a.xaxis ? a.xaxis[i] : float(i % a.w), cy = a.xaxis ? 0.0f : float(i / a.w);
+        Mo::geometry(q, cx, cy, g);
+        Mo::expo(q, g, e);
+        Mo::jac(q, g, e, J);
+        float wgt = 1.0f;
+        if (a.kind == 1) {
+            const float f = Mo::value(q, e);
+            wgt = f > 0.0f ? f_rcp(f) : 0.0f;
+        }
+        acc.add(J, wgt, 0.0f);
+    }
+    ln.template sum_all<NT<P>::value>(acc.A);
+    if (!active || ln.lane != 0) return;
+    float U[NT<P>::value], zero[P], col[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) zero[k] = 0.0f;
+    const bool ok = chol_factor<P>(acc.A, zero, 0.0f, U);
+#pragma unroll
+    for (int c = 0; c < P; ++c) {
+        float rhs[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) rhs[k] = k == c ? -1.0f : 0.0f;
+        chol_solve_neg<P>(U, rhs, col);
+#pragma unroll
+        for (int k = 0; k < P; ++k) a.pcov[(fit * P + k) * P + c] = ok ? col[k] : __int_as_float(0x7fc00000);
+    }
+}
+
+template <class Mo>
+int launch_cov(const CovArgs& a, cudaStream_t stream) {
+    const long long threads = a.n_fits * 8;
+    const long long grid = (threads + 127) / 128;
+    if (grid > 0) dphlm_cov_kernel<Mo><<<(unsigned)grid, 128, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 struct DeviceCtx {
     std::mutex mu;
     unsigned long long* counters = nullptr;
@@ -401,6 +471,9 @@ int launch_gauss2d_elliptical(int G, bool mle, const KArgs& a, DeviceCtx* ctx, c
 int launch_multi_exp1(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp2(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp3(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
+int launch_cov_gauss2d(const CovArgs& a, cudaStream_t s);
+int launch_cov_gauss2d_elliptical(const CovArgs& a, cudaStream_t s);
+int launch_cov_multi_exp(int n_param, const CovArgs& a, cudaStream_t s);
 
 #define DPH_DISPATCH_G(MO, G, mle, a, ctx, s)                                                      \
     switch (G) {                                                                                   \

@@ -20,7 +20,7 @@ from . import _lib, models
 
 FTOL = XTOL = 1.49012e-8
 
-BatchResult = namedtuple("BatchResult", "popt info nfev chisq p_ls counts")
+BatchResult = namedtuple("BatchResult", "popt info nfev chisq p_ls counts pcov", defaults=(None,))
 
 _MESSAGES = {  # dphtools/utils/lm.py:310-353 (taken over from scipy.optimize.leastsq)
     1: "Both actual and predicted relative reductions in the sum of squares are at most {ftol}",
@@ -73,7 +73,8 @@ def _check(rc):
 
 
 def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
-                    factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None, timing=False, out=None):
+                    factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None, timing=False, out=None,
+                    return_pcov=None):
     """Fit ``N`` independent ROIs / histograms: the batched form of per-ROI
     ``curve_fit(model, xdata, roi.ravel(), p0, jac=model.jac, method=method)`` (``lm.py:510-685``).
 
@@ -86,6 +87,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     p0 : ``[N, P]`` float32 initial guesses.
     xdata : ``multi_exp`` only: the shared ``[M]`` x axis.
     timing : device path only: record CUDA events around the two kernels (``_lib.last_kernel_ms()``).
+    return_pcov : ``"jtj"`` or ``"crlb"``: also return the ``[N, P, P]`` covariances (see :func:`covariance`).
     out : host path only: a ``BatchResult`` of preallocated C-contiguous arrays to write into (use
         :func:`pinned_empty` buffers, for the inputs too, so that the copies run asynchronously).
     device : host path only: CUDA device index, or a list of indices to shard the batch over several
@@ -98,8 +100,11 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     model = _resolve_model(model)
     one_d = model.model_id == models.MODEL_MULTI_EXP
     if _is_torch(data) and data.is_cuda:
-        return _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
-                           return_counts, group_lanes, timing)
+        res = _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
+                          return_counts, group_lanes, timing)
+        if return_pcov:
+            res = res._replace(pcov=covariance(model, res.popt, data.shape[1:], return_pcov, xdata))
+        return res
     if _is_torch(data):
         data = data.numpy()
     if _is_torch(p0):
@@ -121,11 +126,12 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     if out is None:
         out = BatchResult(
             np.empty((n, n_param), np.float32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32),
-            np.empty((n, n_param), np.float32) if return_stage1 else None, np.empty((n, 4), np.int32) if return_counts else None,
+            np.empty((n, n_param), np.float32) if return_stage1 else None, np.empty((n, 4), np.int32) if return_counts else None, None,
         )
     else:
         want = [((n, n_param), np.float32), ((n,), np.int32), ((n,), np.int32), ((n,), np.float32),
                 ((n, n_param), np.float32) if return_stage1 else None, ((n, 4), np.int32) if return_counts else None]
+        out = BatchResult(*(tuple(out) + (None,) * (7 - len(out))))
         for a, w in zip(out, want):
             if w is not None and (a is None or a.shape != w[0] or a.dtype != w[1] or not a.flags.c_contiguous):
                 raise ValueError("out: expected a C-contiguous %s array of shape %s" % (np.dtype(w[1]).name, w[0]))
@@ -135,7 +141,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         d = _fill_desc(model, method, n_param, dim0, dim1, hi - lo, ftol, xtol, gtol, maxfev, factor, group_lanes)
         d.data, d.p0 = data[lo:hi].ctypes.data, p0[lo:hi].ctypes.data
         d.xaxis = xa.ctypes.data if xa is not None else None
-        d.popt, d.info, d.nfev, d.chisq = (a[lo:hi].ctypes.data for a in out[:4])
+        d.popt, d.info, d.nfev, d.chisq = (a[lo:hi].ctypes.data for a in tuple(out)[:4])
         d.p_ls = out.p_ls[lo:hi].ctypes.data if return_stage1 else None
         d.counts = out.counts[lo:hi].ctypes.data if return_counts else None
         return _lib.lib().dphlm_fit_batch_host(ctypes.byref(d), dev)
@@ -158,6 +164,8 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
             t.join()
         if errs:
             raise RuntimeError("dphlm: " + errs[0])
+    if return_pcov:
+        out = out._replace(pcov=covariance(model, out.popt, data.shape[1:], return_pcov, xa))
     return out
 
 
@@ -221,7 +229,43 @@ def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev,
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _check(_lib.lib().dphlm_fit_batch(ctypes.byref(d), ctypes.c_void_p(stream)))
-    return BatchResult(popt, info, nfev, chisq, p_ls, counts)
+    return BatchResult(popt, info, nfev, chisq, p_ls, counts, None)
+
+
+def covariance(model, popt, shape, kind="jtj", xdata=None):
+    """Batched parameter covariance from the model Jacobian at ``popt`` (``[N, P]``): ``[N, P, P]``.
+
+    ``kind="jtj"``: ``pinv(J^T J)`` of the unweighted Jacobian -- the ``pcov`` the reference's ``curve_fit`` returns
+    (``lm.py:672-677``).  ``kind="crlb"``: ``(J^T diag(1/f) J)^-1``, the Poisson Cramer-Rao bound.  ``shape`` is the ROI
+    ``(H, W)`` or ``(M,)`` for ``multi_exp`` (which also needs ``xdata``).  CUDA tensors stay on the device (asynchronous on
+    the current stream); numpy input is staged through torch and returned as numpy.
+    """
+    import torch
+
+    model = _resolve_model(model)
+    kinds = {"jtj": 0, "crlb": 1}
+    if kind not in kinds:
+        raise ValueError("kind must be 'jtj' or 'crlb'")
+    as_numpy = not _is_torch(popt)
+    pt = torch.as_tensor(popt, dtype=torch.float32)
+    if not pt.is_cuda:
+        pt = pt.cuda()
+    pt = pt.contiguous()
+    n, n_param = pt.shape
+    shape = tuple(shape)
+    dim0, dim1 = (shape[0], 1) if len(shape) == 1 else shape
+    d = _fill_desc(model, "mle", n_param, dim0, dim1, n, FTOL, XTOL, 0.0, None, 100.0, 0)
+    xa = None
+    if model.model_id == models.MODEL_MULTI_EXP:
+        if xdata is None:
+            raise ValueError("multi_exp needs xdata")
+        xa = torch.as_tensor(np.asarray(xdata, dtype=np.float32), device=pt.device).contiguous()
+        d.xaxis = xa.data_ptr()
+    pcov = torch.empty((n, n_param, n_param), dtype=torch.float32, device=pt.device)
+    with torch.cuda.device(pt.device):
+        stream = torch.cuda.current_stream(pt.device).cuda_stream
+        _check(_lib.lib().dphlm_covariance(ctypes.byref(d), pt.data_ptr(), pcov.data_ptr(), kinds[kind], ctypes.c_void_p(stream)))
+    return pcov.cpu().numpy() if as_numpy else pcov
 
 
 def _grid_shape(xdata):

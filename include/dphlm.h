@@ -74,6 +74,14 @@ int dphlm_fit_batch(const dphlm_desc* d, void* stream);
  * returns when they are in place.  Large batches are cut into chunks whose copies overlap the kernels. */
 int dphlm_fit_batch_host(const dphlm_desc* d, int device);
 
+/* Parameter covariance of every fit from the model Jacobian at `popt` (DEVICE pointers, asynchronous on `stream`;
+ * uses model, n_param, dim0, dim1, n_fits, xaxis of the descriptor).  pcov is [n_fits, n_param, n_param].
+ *   DPHLM_COV_JTJ   pinv(J^T J) of the unweighted Jacobian: the `pcov` curve_fit returns (lm.py:672-677)
+ *   DPHLM_COV_CRLB  (J^T diag(1/f) J)^-1: the Poisson Cramer-Rao bound of the fitted parameters
+ * A rank-deficient matrix gives NaNs (the reference drops its small singular values instead). */
+enum dphlm_cov_kind { DPHLM_COV_JTJ = 0, DPHLM_COV_CRLB = 1 };
+int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int kind, void* stream);
+
 /* Page-locked host buffers for dphlm_fit_batch_host (plain malloc'ed memory works too, slower). */
 void* dphlm_host_alloc(size_t bytes);
 void dphlm_host_free(void* p);

@@ -168,3 +168,30 @@ def test_straggler_handoff_changes_nothing_beyond_rounding(golden):
     for o in outs:
         rep = parity_report("gauss2d", o, g)
         assert rep["converged_equal"] == 1.0 and rep["info_equal"] >= 0.995 and rep["within_rtol"] >= 0.999, rep
+
+
+@pytest.mark.parametrize("name", ["c2_mle", "c4_ls", "c5_mle"])
+def test_batched_covariance_matches_reference_pcov(golden, name):
+    """dphlm_covariance(kind=JTJ) against the reference's pcov = pinv(J^T J) (lm.py:672-677) and kind=CRLB against the
+    float64 inverse Fisher matrix, both from the Jacobian at popt."""
+    g = golden(name)
+    model = models.BUILTIN[g["model"]]
+    n = 300
+    shape = g["data"].shape[1:]
+    xd = g["xaxis"].astype(float) if g["xaxis"] is not None else models.roi_grid(*shape)
+    popt = g["popt"][:n].astype(np.float32)
+    got = dph.covariance(model, popt, shape, "jtj", g["xaxis"])
+    crlb = dph.covariance(model, torch.from_numpy(popt).cuda(), shape, "crlb", g["xaxis"]).cpu().numpy()
+    for i in range(0, n, 7):
+        J = model.jac(xd, *popt[i].astype(float))
+        ref = lm_oracle.pcov_from_jac(J)
+        scale = np.sqrt(np.outer(np.diag(ref), np.diag(ref)))
+        assert np.abs((got[i] - ref) / scale).max() < 2e-3, (i, got[i], ref)
+        f = model(xd, *popt[i].astype(float))
+        fisher = (J.T / f) @ J
+        ref2 = np.linalg.inv(fisher)
+        scale2 = np.sqrt(np.outer(np.diag(ref2), np.diag(ref2)))
+        assert np.abs((crlb[i] - ref2) / scale2).max() < 2e-3
+    r = dph.curve_fit_batch(model, torch.from_numpy(g["data"][:64]).cuda(), torch.from_numpy(g["p0"][:64]).cuda(), g["method"],
+                            g["xaxis"], return_pcov="crlb")
+    assert r.pcov.shape == (64, popt.shape[1], popt.shape[1]) and torch.isfinite(r.pcov).all()
