@@ -1,6 +1,7 @@
 """B200-native batched Levenberg-Marquardt / Poisson-MLE fitter (drop-in for ``dphtools.utils.lm``)."""
 
-from . import models, synth  # noqa: F401
+from . import fitfuncs, models, synth  # noqa: F401
+from .fitfuncs import exponent_fit, multi_exp_fit, multi_exp_fit_batch  # noqa: F401
 from .lm import BatchResult, covariance, curve_fit, curve_fit_batch, pinned_empty  # noqa: F401
 from .models import gauss2d, gauss2d_elliptical, multi_exp  # noqa: F401
 

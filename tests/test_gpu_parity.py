@@ -195,3 +195,19 @@ def test_batched_covariance_matches_reference_pcov(golden, name):
     r = dph.curve_fit_batch(model, torch.from_numpy(g["data"][:64]).cuda(), torch.from_numpy(g["p0"][:64]).cuda(), g["method"],
                             g["xaxis"], return_pcov="crlb")
     assert r.pcov.shape == (64, popt.shape[1], popt.shape[1]) and torch.isfinite(r.pcov).all()
+
+
+def test_multi_exp_fit_driver_on_gpu(golden):
+    """The reference's only in-package caller of curve_fit (fitfuncs.py:93-159) with method='mle' on the GPU."""
+    from dphtools_b200 import fitfuncs
+
+    g = golden("c5_mle")
+    t = g["xaxis"].astype(float)
+    y = g["data"][3].astype(float)
+    popt, pcov = fitfuncs.multi_exp_fit(y[1:], t[1:], components=2, method="mle")  # t > 0 for the log-spaced split
+    p0 = fitfuncs.guess_multi_exp(y[1:], t[1:], 2)
+    ref = lm_oracle.curve_fit(models.multi_exp, t[1:], y[1:], p0, models.multi_exp_jac, "mle")[0]
+    np.testing.assert_allclose(popt, ref, rtol=1e-4)
+    res, p0b = fitfuncs.multi_exp_fit_batch(g["data"][:200, 1:], t[1:], 2, method="mle")
+    assert ((res.info >= 1) & (res.info <= 4)).mean() > 0.99
+    np.testing.assert_allclose(res.popt[3], ref, rtol=1e-4)
