@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("DPHLM_LIB") or os.path.join(os.path.dirname(os.path.a
 
 SYMBOLS = [
     "dphlm_desc_init", "dphlm_fit_batch", "dphlm_fit_batch_host", "dphlm_host_alloc", "dphlm_host_free",
-    "dphlm_device_count", "dphlm_version", "dphlm_last_error", "dphlm_last_kernel_ms", "dphlm_covariance",
+    "dphlm_device_count", "dphlm_version", "dphlm_last_error", "dphlm_last_kernel_ms", "dphlm_covariance", "dphlm_extract_rois",
 ]
 
 
@@ -27,6 +27,17 @@ class Desc(ctypes.Structure):
         ("p_ls", ctypes.c_void_p), ("counts", ctypes.c_void_p),
         ("ftol", ctypes.c_float), ("xtol", ctypes.c_float), ("gtol", ctypes.c_float), ("factor", ctypes.c_float),
         ("maxfev", ctypes.c_int32), ("flags", ctypes.c_int32),
+    ]
+
+
+class ExtractDesc(ctypes.Structure):
+    """Mirror of ``struct dphlm_extract_desc``."""
+
+    _fields_ = [
+        ("frames", ctypes.c_void_p), ("frame_dtype", ctypes.c_int32), ("n_frames", ctypes.c_int32),
+        ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("peaks", ctypes.c_void_p), ("n_peaks", ctypes.c_int64),
+        ("roi", ctypes.c_int32), ("refine", ctypes.c_int32), ("sigma0", ctypes.c_float),
+        ("rois", ctypes.c_void_p), ("p0", ctypes.c_void_p), ("valid", ctypes.c_void_p),
     ]
 
 
@@ -50,6 +61,8 @@ def lib():
         L.dphlm_fit_batch_host.restype = ctypes.c_int
         L.dphlm_covariance.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.dphlm_covariance.restype = ctypes.c_int
+        L.dphlm_extract_rois.argtypes = [ctypes.POINTER(ExtractDesc), ctypes.c_void_p]
+        L.dphlm_extract_rois.restype = ctypes.c_int
         L.dphlm_host_alloc.argtypes = [ctypes.c_size_t]
         L.dphlm_host_alloc.restype = ctypes.c_void_p
         L.dphlm_host_free.argtypes = [ctypes.c_void_p]

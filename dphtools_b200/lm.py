@@ -268,6 +268,39 @@ def covariance(model, popt, shape, kind="jtj", xdata=None):
     return pcov.cpu().numpy() if as_numpy else pcov
 
 
+def extract_rois(frames, peaks, roi=11, sigma0=1.3, refine=False):
+    """Cut ``roi x roi`` windows around ``peaks`` (``[N, 3]`` int32: frame, row, column) out of ``frames``
+    (``[F, H, W]`` float32 or uint16/int16 camera counts) and derive the ``gauss2d`` initial guesses, on the device.
+
+    Window and guess follow ``slice_maker`` / ``localize_peak`` of the reference (``dphtools/utils/__init__.py:244-295,
+    590-617``); see ``include/dphlm.h``.  Returns CUDA tensors ``(rois[N,roi,roi] float32, p0[N,5], valid[N] bool)`` ready
+    for :func:`curve_fit_batch`; numpy inputs are staged through torch.
+    """
+    import torch
+
+    fr = torch.as_tensor(frames)
+    if fr.dtype in (torch.uint16, torch.int16):
+        fr, code = fr.view(torch.int16) if fr.dtype == torch.uint16 else fr, 1
+    else:
+        fr, code = fr.float(), 0
+    fr = fr.cuda().contiguous()
+    pk = torch.as_tensor(peaks, dtype=torch.int32).to(fr.device).contiguous()
+    if fr.dim() != 3 or pk.dim() != 2 or pk.shape[1] != 3:
+        raise ValueError("frames must be [F,H,W] and peaks [N,3] (frame, row, column)")
+    n = pk.shape[0]
+    rois = torch.empty((n, roi, roi), dtype=torch.float32, device=fr.device)
+    p0 = torch.empty((n, 5), dtype=torch.float32, device=fr.device)
+    valid = torch.empty(n, dtype=torch.int32, device=fr.device)
+    d = _lib.ExtractDesc()
+    d.frames, d.frame_dtype, d.n_frames, d.height, d.width = fr.data_ptr(), code, fr.shape[0], fr.shape[1], fr.shape[2]
+    d.peaks, d.n_peaks, d.roi, d.refine, d.sigma0 = pk.data_ptr(), n, roi, int(bool(refine)), sigma0
+    d.rois, d.p0, d.valid = rois.data_ptr(), p0.data_ptr(), valid.data_ptr()
+    with torch.cuda.device(fr.device):
+        stream = torch.cuda.current_stream(fr.device).cuda_stream
+        _check(_lib.lib().dphlm_extract_rois(ctypes.byref(d), ctypes.c_void_p(stream)))
+    return rois, p0, valid.bool()
+
+
 def _grid_shape(xdata):
     """(h, w) if ``xdata`` is the (2, M) pixel grid of :func:`models.roi_grid`, else None."""
     if xdata.ndim != 2 or xdata.shape[0] != 2:

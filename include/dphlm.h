@@ -82,6 +82,28 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device);
 enum dphlm_cov_kind { DPHLM_COV_JTJ = 0, DPHLM_COV_CRLB = 1 };
 int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int kind, void* stream);
 
+/* The step upstream of the fit: cut roi x roi windows around peak positions out of a stack of frames and derive
+ * the Gaussian initial guesses on the device (DEVICE pointers, asynchronous on `stream`).
+ * Window = slice_maker's (dphtools/utils/__init__.py:244-295): rows [row - roi/2, row - roi/2 + roi), same for columns.
+ * p0 = (max - min, x0, y0, sigma0, max(min, 0.5)) with (x0, y0) the ROI centre or, with refine != 0, the vertex of the
+ * parabolas through the centre row / column (localize_peak, dphtools/utils/__init__.py:590-617), in ROI coordinates.
+ * A window crossing the frame border is filled by clamping and reported with valid = 0. */
+enum dphlm_dtype { DPHLM_F32 = 0, DPHLM_U16 = 1 };
+typedef struct dphlm_extract_desc {
+    const void* frames;    /* [n_frames, height, width], float32 or uint16 (camera counts) */
+    int32_t frame_dtype;   /* enum dphlm_dtype */
+    int32_t n_frames, height, width;
+    const int32_t* peaks;  /* [n_peaks, 3]: frame, row, column of the peak pixel */
+    int64_t n_peaks;
+    int32_t roi;           /* window size, 1..31 */
+    int32_t refine;        /* 0: centre of the window; 1: parabola vertex */
+    float sigma0;          /* initial width */
+    float* rois;           /* out [n_peaks, roi, roi] float32: `data` of dphlm_fit_batch */
+    float* p0;             /* out [n_peaks, 5]:            `p0`   of dphlm_fit_batch (DPHLM_GAUSS2D) */
+    int32_t* valid;        /* out [n_peaks], optional */
+} dphlm_extract_desc;
+int dphlm_extract_rois(const dphlm_extract_desc* d, void* stream);
+
 /* Page-locked host buffers for dphlm_fit_batch_host (plain malloc'ed memory works too, slower). */
 void* dphlm_host_alloc(size_t bytes);
 void dphlm_host_free(void* p);

@@ -211,3 +211,49 @@ def test_multi_exp_fit_driver_on_gpu(golden):
     res, p0b = fitfuncs.multi_exp_fit_batch(g["data"][:200, 1:], t[1:], 2, method="mle")
     assert ((res.info >= 1) & (res.info <= 4)).mean() > 0.99
     np.testing.assert_allclose(res.popt[3], ref, rtol=1e-4)
+
+
+def test_roi_extraction_and_guess_then_fit():
+    """Frames + peak list -> ROIs + p0 on the device (dphlm_extract_rois) -> fit.  The window is slice_maker's, the guess
+    the C1 recipe, the refined centre localize_peak's parabola (checked against np.polyfit as the reference uses it)."""
+    rng = np.random.default_rng(5)
+    F, H, W, roi = 3, 96, 128, 11
+    frames = rng.poisson(4.0, size=(F, H, W)).astype(np.float32)
+    xy = models.roi_grid(H, W)
+    # a jittered grid (spots do not overlap) that includes positions hanging over the frame border
+    gr, gc = np.meshgrid(np.arange(2, H, 16), np.arange(3, W, 16), indexing="ij")
+    peaks = np.concatenate([np.stack([np.full(gr.size, f), gr.ravel() + rng.integers(-1, 2, gr.size),
+                                      gc.ravel() + rng.integers(-1, 2, gc.size)], axis=1) for f in range(F)]).astype(np.int32)
+    n = peaks.shape[0]
+    truth = []
+    for f, r, c in peaks:
+        cx, cy = c + rng.uniform(-0.4, 0.4), r + rng.uniform(-0.4, 0.4)
+        frames[f] += rng.poisson(models.gauss2d(xy, 300.0, cx, cy, 1.3, 0.0)).reshape(H, W)
+        truth.append((cx, cy))
+    frames_u16 = frames.astype(np.uint16)
+    for fr in (frames, frames_u16):
+        rois, p0, valid = dph.extract_rois(fr, peaks, roi=roi, refine=True)
+        rois, p0, valid = rois.cpu().numpy(), p0.cpu().numpy(), valid.cpu().numpy()
+        half = roi // 2
+        for k in range(n):
+            f, r, c = peaks[k]
+            inside = r - half >= 0 and c - half >= 0 and r - half + roi <= H and c - half + roi <= W
+            assert bool(valid[k]) == inside
+            if not inside:
+                continue
+            want = frames[f, r - half:r - half + roi, c - half:c - half + roi]  # slice_maker((r, c), roi)
+            np.testing.assert_array_equal(rois[k], want)
+            assert p0[k, 0] == want.max() - want.min() and p0[k, 4] == max(want.min(), 0.5) and p0[k, 3] == np.float32(1.3)
+            t = np.arange(roi) - half
+            fx, fy = np.polyfit(t, want[half, :], 2), np.polyfit(t, want[:, half], 2)  # localize_peak
+            if fx[0] < 0:
+                np.testing.assert_allclose(p0[k, 1], np.clip(half - fx[1] / (2 * fx[0]), 0, roi - 1), rtol=2e-4, atol=2e-4)
+            if fy[0] < 0:
+                np.testing.assert_allclose(p0[k, 2], np.clip(half - fy[1] / (2 * fy[0]), 0, roi - 1), rtol=2e-4, atol=2e-4)
+    rois_t, p0_t, valid_t = dph.extract_rois(frames_u16, peaks, roi=roi)
+    res = dph.curve_fit_batch(models.gauss2d, rois_t, p0_t, "mle")
+    ok = valid_t.cpu().numpy() & (res.info.cpu().numpy() > 0)
+    popt = res.popt.cpu().numpy()
+    err = np.array([(popt[k, 1] + peaks[k, 2] - roi // 2 - truth[k][0], popt[k, 2] + peaks[k, 1] - roi // 2 - truth[k][1]) for k in range(n)])
+    isolated = ok & (np.abs(err).max(1) < 1.0)  # overlapping random spots excluded
+    assert isolated.sum() >= 0.95 * ok.sum() and ok.sum() > 0.6 * n and np.median(np.abs(err[isolated])) < 0.08
