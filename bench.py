@@ -183,6 +183,15 @@ def main():
     sampler.ready.wait(timeout=30)
     for i in range(args.warmup):
         step(i)
+    # an idle B200 sits at ~120 MHz and needs tens of milliseconds of load to reach its boost clock: keep the
+    # (untimed) warm-up going for at least half a second so that the timed steps do not include the ramp
+    t_warm = time.perf_counter()
+    i = args.warmup
+    while time.perf_counter() - t_warm < 0.5:
+        step(i)
+        i += 1
+        if i % 8 == 0:
+            torch.cuda.synchronize()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active = True
@@ -267,10 +276,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": n * (ROI * ROI + 5) * 4,
                     "d2h_bytes_per_step": n * (5 + 3) * 4, "steps": e2e_steps, "host_memory": "pinned inputs and outputs (dphtools_b200.pinned_empty)",
                     "converged_fraction": float(((r_host.info >= 1) & (r_host.info <= 4)).mean())},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": 4 * args.steps,  # pre-fit + lm() main launches and their two straggler follow-ups
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
-                "traffic": None, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; with its straggler follow-up launches)",
+                # dram__bytes_read+write of the lm() main launch from the ncu --set full capture of this workload
+                # (profiles/r1_ncu_full_final_gauss2d_11x11_G4.txt); algorithmic: 484 B/fit read again + 32 B/fit written
+                "traffic": 51.2e6 * n / 1e5, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; with its straggler follow-up launches)",
                 "kernel_ms": k_main * 1e3, "share_of_step": k_main / k_s,
                 "peak_source": "SMs x 128 lanes x 2 x max SM clock (no fp32 entry in MEASURED_PEAKS.json)",
                 "flops_per_fit": float(np.mean(fl_main)) / n,
