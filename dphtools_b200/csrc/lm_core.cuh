@@ -33,7 +33,13 @@
 #define DPH_HD inline
 #endif
 
+#ifndef DPH_PAIR_UNROLL
+#define DPH_PAIR_UNROLL 1  // unroll factor of the pixel-pair loop (registers vs instruction-level parallelism)
+#endif
+
 namespace dphlm {
+
+constexpr int kPairUnroll = DPH_PAIR_UNROLL;
 
 // ------------------------------------------------------------------------------------------ math
 #if defined(__CUDA_ARCH__)
@@ -589,7 +595,7 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
         a2.clear();
         const int npair = px.M >> 1;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+#pragma unroll kPairUnroll
 #endif
         for (int q = ln.lane; q < npair; q += G) {
             const int i = 2 * q;

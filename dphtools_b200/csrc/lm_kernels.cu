@@ -30,8 +30,7 @@ int get_ctx(int dev, DeviceCtx** out) {
     if (dev < 0 || dev >= 64) return fail("device index out of range");
     DeviceCtx& c = g_ctx[dev];
     std::lock_guard<std::mutex> lk(c.mu);
-    if (!c.counters) {
-        CUDA_TRY(cudaMalloc(&c.counters, kCounterRing * sizeof(unsigned long long)));
+    if (!c.sms) {
         CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
         cudaMemPool_t pool;
         unsigned long long keep = ~0ull;
@@ -138,7 +137,9 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     if (!d->p_ls) a.p_ls = reinterpret_cast<float*>(ws + b_ier + b_park);
     // straggler lists (DPHLM_FLAG_NO_HANDOFF: keep every fit in the group that started it)
     a.park_cap = (d->flags & DPHLM_FLAG_NO_HANDOFF) ? 0 : park_capacity(d->n_fits);
+    // 256-byte header, zeroed once: the two park counters and the four work counters of the launches
     a.park_count = reinterpret_cast<int*>(ws + b_ier);
+    a.counter = reinterpret_cast<unsigned long long*>(ws + b_ier + 64);
     a.park_idx = a.park_count + 64;
     a.park_rec = reinterpret_cast<float*>(a.park_idx + 2 * (size_t)park_capacity(d->n_fits));
     CUDA_TRY(cudaMemsetAsync(a.park_count, 0, 256, s));

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -358,8 +359,6 @@ int launch_cov(const CovArgs& a, cudaStream_t stream) {
 
 struct DeviceCtx {
     std::mutex mu;
-    unsigned long long* counters = nullptr;
-    unsigned next = 0;
     int sms = 0;
     // host-path staging buffers, one set per pipeline slot
     struct Slot {
@@ -376,7 +375,6 @@ struct DeviceCtx {
     } sides[4];
     unsigned next_side = 0;
 };
-constexpr int kCounterRing = 1024;
 
 template <class Kern>
 int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream, long long work = -1) {
@@ -403,13 +401,7 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
         }
         occ = c.occ;
     }
-    unsigned slot;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        slot = ctx->next++ % kCounterRing;
-    }
-    a.counter = ctx->counters + slot;
-    CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), stream));
+    // a.counter points into the call's own workspace header (zeroed once per call by fit_device)
     long long grid = (long long)ctx->sms * occ;
     if (work < 0) work = a.n_fits;
     const long long need = (work + (long long)kWarps * fpw - 1) / ((long long)kWarps * fpw);
@@ -423,6 +415,10 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
 // both stages of curve_fit(method='ls'|'mle') for one batch: pre-fit kernel, then the lm() kernel, each followed
 // by a small warp-per-fit launch that finishes the stragglers the main kernel parked
 constexpr int kBudgetPrefit = 16, kBudgetMain = 24;  // ~p99.9 of the trip counts (mean 7 and 9.7)
+inline int budget_from_env(const char* name, int dflt) {  // tuning aid: DPHLM_BUDGET_A / DPHLM_BUDGET_B
+    const char* e = getenv(name);
+    return e && atoi(e) > 0 ? atoi(e) : dflt;
+}
 
 template <class Mo, bool MLE, int G>
 int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
@@ -434,8 +430,10 @@ int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
     using SA = StageA<Mo>;
     using SB = StageB<Mo, MLE>;
     KArgs a = a0;
-    a.budget = handoff ? kBudgetPrefit : 0;
+    a.budget = handoff ? budget_from_env("DPHLM_BUDGET_A", kBudgetPrefit) : 0;
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[0], stream));
+    unsigned long long* const counters = a0.counter;  // four work counters, one per launch
+    a.counter = counters;
     int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream);
     if (rc) return rc;
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
@@ -443,11 +441,13 @@ int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
     // The straggler launch stays on the caller's stream, directly behind the pre-fit kernel, so that its few CTAs
     // are resident before the persistent lm() kernel -- sent through the side stream -- takes every remaining slot.
     KArgs b = a;
-    b.budget = handoff ? kBudgetMain : 0;
+    b.counter = counters + 2;
+    b.budget = handoff ? budget_from_env("DPHLM_BUDGET_B", kBudgetMain) : 0;
     b.park_count += 1; b.park_idx += a.park_cap; b.park_rec += (size_t)a.park_cap * kParkRecord;
     if (handoff) {
         DeviceCtx::Side& sd = ctx->sides[ctx->next_side++ % 4];  // the caller holds ctx->fork_mu
         CUDA_TRY(cudaEventRecord(sd.fork_ev, stream));
+        a.counter = counters + 1;
         rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, a, 1, smem_w, ctx, stream, a.park_cap);
         if (rc) return rc;
         CUDA_TRY(cudaStreamWaitEvent(sd.stream, sd.fork_ev, 0));
@@ -455,6 +455,7 @@ int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(sd.join_ev, sd.stream));
         CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_ev, 0));
+        b.counter = counters + 3;
         rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, b, 1, smem_w, ctx, stream, 2 * a.park_cap);
         if (rc) return rc;
     } else {

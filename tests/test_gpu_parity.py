@@ -257,3 +257,17 @@ def test_roi_extraction_and_guess_then_fit():
     err = np.array([(popt[k, 1] + peaks[k, 2] - roi // 2 - truth[k][0], popt[k, 2] + peaks[k, 1] - roi // 2 - truth[k][1]) for k in range(n)])
     isolated = ok & (np.abs(err).max(1) < 1.0)  # overlapping random spots excluded
     assert isolated.sum() >= 0.95 * ok.sum() and ok.sum() > 0.6 * n and np.median(np.abs(err[isolated])) < 0.08
+
+
+def test_many_small_asynchronous_calls(golden):
+    """Hundreds of small calls enqueued without synchronisation (private per-call counters and workspaces)."""
+    g = golden("c2_mle")
+    data, p0 = torch.from_numpy(g["data"][:4096]).cuda(), torch.from_numpy(g["p0"][:4096]).cuda()
+    whole = dph.curve_fit_batch(models.gauss2d, data, p0, "mle")
+    parts = [dph.curve_fit_batch(models.gauss2d, data[k:k + 16], p0[k:k + 16], "mle") for k in range(0, 4096, 16)]
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        other = [dph.curve_fit_batch(models.gauss2d, data[k:k + 64], p0[k:k + 64], "mle") for k in range(0, 4096, 64)]
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([p.popt for p in parts]), whole.popt) and torch.equal(torch.cat([p.info for p in parts]), whole.info)
+    assert torch.equal(torch.cat([p.popt for p in other]), whole.popt)
