@@ -271,3 +271,20 @@ def test_many_small_asynchronous_calls(golden):
     torch.cuda.synchronize()
     assert torch.equal(torch.cat([p.popt for p in parts]), whole.popt) and torch.equal(torch.cat([p.info for p in parts]), whole.info)
     assert torch.equal(torch.cat([p.popt for p in other]), whole.popt)
+
+
+@pytest.mark.parametrize("kw", [dict(ftol=1e-6, xtol=1e-6), dict(maxfev=12), dict(gtol=1e-2)])
+def test_keywords_reach_both_stages_on_gpu(golden, kw):
+    """ftol / xtol / gtol / maxfev go to the pre-fit and to lm() (lm.py:643, 668): same exits as the oracle."""
+    g = golden("c2_mle")
+    n = 150
+    r = dph.curve_fit_batch(models.gauss2d, torch.from_numpy(g["data"][:n]).cuda(), torch.from_numpy(g["p0"][:n]).cuda(), "mle", **kw)
+    info, popt = r.info.cpu().numpy(), r.popt.cpu().numpy()
+    ref = lm_oracle.fit_batch(models.gauss2d, g["data"][:n], g["p0"][:n], "mle", models.roi_grid(11, 11), **kw)
+    conv_o, conv_r = (info >= 1) & (info <= 4), (ref["info"] >= 1) & (ref["info"] <= 4)
+    assert (conv_o == conv_r).mean() >= 0.98
+    both = conv_o & conv_r
+    assert (info[both] == ref["info"][both]).mean() >= 0.97
+    rel = np.abs(popt[both][:, :4] - ref["popt"][both][:, :4]) / np.abs(ref["popt"][both][:, :4])
+    assert np.quantile(rel.max(1), 0.99) < 1e-4
+    assert (np.sign(info[~conv_o]) == np.sign(ref["info"][~conv_o])).all()

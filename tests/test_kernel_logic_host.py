@@ -27,3 +27,24 @@ def test_host_build_of_kernel_core_matches_reference(golden, name, min_info, min
     ok = np.isfinite(g["p_ls"]).all(1)
     rel = np.abs(out["p_ls"][ok] - g["p_ls"][ok]) / np.abs(g["p_ls"][ok])
     assert np.quantile(rel.max(1), 0.99) < 1e-4
+
+
+@pytest.mark.parametrize("kw", [dict(ftol=1e-6, xtol=1e-6), dict(maxfev=12), dict(gtol=1e-2), dict(ftol=1e-10, xtol=1e-10, maxfev=80)])
+def test_keywords_reach_both_stages_like_the_reference(golden, kw):
+    """ftol / xtol / gtol / maxfev are forwarded to the pre-fit AND to lm() (lm.py:643, 668; quirks Q1, Q13, Q14):
+    same exits as the float64 oracle with the same keywords, including the failures (scipy raises -> info < 0,
+    lm() out of trips -> info 5)."""
+    from oracle import lm_oracle
+
+    g = golden("c2_mle")
+    n = 150
+    out = host_emu.fit_batch(0, "mle", g["data"][:n], g["p0"][:n], None, ftol=kw.get("ftol", 1.49012e-8), xtol=kw.get("xtol", 1.49012e-8),
+                             gtol=kw.get("gtol", 0.0), maxfev=kw.get("maxfev", 0))
+    ref = lm_oracle.fit_batch(models.gauss2d, g["data"][:n], g["p0"][:n], "mle", models.roi_grid(11, 11), **kw)
+    conv_o, conv_r = (out["info"] >= 1) & (out["info"] <= 4), (ref["info"] >= 1) & (ref["info"] <= 4)
+    assert (conv_o == conv_r).mean() >= 0.98, (out["info"][:20], ref["info"][:20])
+    both = conv_o & conv_r
+    assert (out["info"][both] == ref["info"][both]).mean() >= 0.97
+    rel = np.abs(out["popt"][both][:, :4] - ref["popt"][both][:, :4]) / np.abs(ref["popt"][both][:, :4])
+    assert np.quantile(rel.max(1), 0.99) < 1e-4
+    assert (np.sign(out["info"][~conv_o]) == np.sign(ref["info"][~conv_o])).all()  # pre-fit failure vs lm() failure
