@@ -1,6 +1,7 @@
 """Batch-vectorised numpy emulation of the CUDA kernel's ALGORITHM at a chosen precision.  TEST INFRASTRUCTURE.
 
-There is no GPU in the build container, so the numerics of the fp32 kernel (differential chi-square
+PROTOTYPE of the numerics study (the production algorithm is dphtools_b200/csrc/lm_core.cuh, whose host build is
+oracle/host_emu).  There is no GPU in the build container, so the numerics of the fp32 kernel (differential chi-square
 evaluation, tight normal-equation LS pre-fit, the reference's lambda schedule and accept/reject quirks)
 are developed and regression-tested here against the float64 oracle.  The CUDA kernels in
 ``dphtools_b200/csrc/`` implement the same steps; this file is their executable specification, never a
