@@ -24,7 +24,7 @@ class Desc(ctypes.Structure):
         ("n_fits", ctypes.c_int64),
         ("data", ctypes.c_void_p), ("xaxis", ctypes.c_void_p), ("p0", ctypes.c_void_p),
         ("popt", ctypes.c_void_p), ("info", ctypes.c_void_p), ("nfev", ctypes.c_void_p), ("chisq", ctypes.c_void_p),
-        ("p_ls", ctypes.c_void_p), ("counts", ctypes.c_void_p),
+        ("p_ls", ctypes.c_void_p), ("counts", ctypes.c_void_p), ("x_acc", ctypes.c_void_p),
         ("ftol", ctypes.c_float), ("xtol", ctypes.c_float), ("gtol", ctypes.c_float), ("factor", ctypes.c_float),
         ("maxfev", ctypes.c_int32), ("flags", ctypes.c_int32),
     ]

@@ -117,7 +117,7 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     KArgs a{};
     a.data = d->data; a.xaxis = d->xaxis; a.p0 = d->p0;
     a.popt = d->popt; a.info = d->info; a.nfev = d->nfev; a.chisq = d->chisq;
-    a.p_ls = d->p_ls; a.counts = d->counts;
+    a.p_ls = d->p_ls; a.counts = d->counts; a.x_acc = d->x_acc;
     a.n_fits = d->n_fits; a.h = d->dim0; a.w = d->dim1;
     a.opt = Options{d->ftol, d->xtol, d->gtol, d->factor, d->maxfev};
     if (d->flags & DPHLM_FLAG_TIMING) {
@@ -205,7 +205,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
                  b_cnt = align_up(chunk * 16), b_x = align_up(M * 4);
     const size_t b_ws = align_up(chunk * 4) + align_up(park_bytes(chunk)) + align_up(chunk * P * 4);
-    const size_t need = b_data + 3 * b_par + 3 * b_i + b_cnt + b_x + b_ws;
+    const size_t need = b_data + 4 * b_par + 3 * b_i + b_cnt + b_x + b_ws;
     int rc = 0;
     // one host call at a time per device: the staging slots are shared
     static std::mutex host_mu[64];
@@ -230,6 +230,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         float* dp0 = (float*)b; b += b_par;
         float* dpopt = (float*)b; b += b_par;
         float* dpls = (float*)b; b += b_par;
+        float* dxacc = (float*)b; b += b_par;
         int* dinfo = (int*)b; b += b_i;
         int* dnfev = (int*)b; b += b_i;
         float* dchi = (float*)b; b += b_i;
@@ -243,6 +244,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         c.popt = dpopt; c.info = dinfo; c.nfev = dnfev; c.chisq = dchi;
         c.p_ls = dpls;  // always materialised in the slot buffer: the lm() kernel starts from it
         c.counts = d->counts ? dcnt : nullptr;
+        c.x_acc = d->x_acc ? dxacc : nullptr;
         rc = fit_device(&c, ctx, s.stream, dws);
         if (rc) break;
         CUDA_TRY(cudaMemcpyAsync(d->popt + lo * P, dpopt, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -251,6 +253,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         CUDA_TRY(cudaMemcpyAsync(d->chisq + lo, dchi, n * 4, cudaMemcpyDeviceToHost, s.stream));
         if (d->p_ls) CUDA_TRY(cudaMemcpyAsync(d->p_ls + lo * P, dpls, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
         if (d->counts) CUDA_TRY(cudaMemcpyAsync(d->counts + lo * 4, dcnt, n * 16, cudaMemcpyDeviceToHost, s.stream));
+        if (d->x_acc) CUDA_TRY(cudaMemcpyAsync(d->x_acc + lo * P, dxacc, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
     }
     for (auto& s : ctx->slots) {
         cudaError_t e = cudaStreamSynchronize(s.stream);

@@ -48,6 +48,7 @@ struct KArgs {
     float* p_ls;   // never null inside the kernels (user buffer or workspace)
     int* ier;      // workspace [n_fits]: exit code of the pre-fit (100 = non-finite input data)
     int* counts;   // optional
+    float* x_acc;  // optional: last accepted point of lm()
     unsigned long long* counter;
     // straggler hand-off: fits that used up `budget` trips are parked here and resumed by a warp-per-fit launch
     int* park_count;   // [1] number of parked fits of this stage (may exceed park_cap: the excess was not parked)
@@ -166,6 +167,10 @@ struct IoDevice {
                         a.nfev[idx] = 0;
                         a.chisq[idx] = 0.0f;
                         if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
+                        if (a.x_acc) {
+#pragma unroll
+                            for (int k = 0; k < P; ++k) a.x_acc[idx * P + k] = pstart[k];
+                        }
                     }
                     if (ln.lane == 0) slot = atomicAdd(a.counter, 1ull);
                     slot = __shfl_sync(ln.gmask, slot, src);
@@ -215,6 +220,10 @@ struct IoDevice {
                         a.nfev[idx] = 0;
                         a.chisq[idx] = 0.0f;
                         if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
+                        if (a.x_acc) {
+#pragma unroll
+                            for (int k = 0; k < P; ++k) a.x_acc[idx * P + k] = pstart[k];
+                        }
                     }
                     continue;
                 }
@@ -254,6 +263,10 @@ struct IoDevice {
         a.nfev[fit] = st.ev;
         a.chisq[fit] = st.chisq_ret;
         if (a.counts) { a.counts[4 * fit + 1] = st.n_acc; a.counts[4 * fit + 2] = st.n_rej; a.counts[4 * fit + 3] = 0; }
+        if (a.x_acc) {
+#pragma unroll
+            for (int k = 0; k < Mo::P; ++k) a.x_acc[fit * Mo::P + k] = st.x[k];
+        }
     }
 };
 

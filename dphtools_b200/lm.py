@@ -20,7 +20,7 @@ from . import _lib, models
 
 FTOL = XTOL = 1.49012e-8
 
-BatchResult = namedtuple("BatchResult", "popt info nfev chisq p_ls counts pcov", defaults=(None,))
+BatchResult = namedtuple("BatchResult", "popt info nfev chisq p_ls counts pcov x_acc", defaults=(None, None))
 
 _MESSAGES = {  # dphtools/utils/lm.py:310-353 (taken over from scipy.optimize.leastsq)
     1: "Both actual and predicted relative reductions in the sum of squares are at most {ftol}",
@@ -74,7 +74,7 @@ def _check(rc):
 
 def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
                     factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None, timing=False, out=None,
-                    return_pcov=None):
+                    return_pcov=None, return_x_acc=False):
     """Fit ``N`` independent ROIs / histograms: the batched form of per-ROI
     ``curve_fit(model, xdata, roi.ravel(), p0, jac=model.jac, method=method)`` (``lm.py:510-685``).
 
@@ -87,6 +87,8 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     p0 : ``[N, P]`` float32 initial guesses.
     xdata : ``multi_exp`` only: the shared ``[M]`` x axis.
     timing : device path only: record CUDA events around the two kernels (``_lib.last_kernel_ms()``).
+    return_x_acc : also return the last ACCEPTED point of ``lm()`` (``[N, P]``): the reference evaluates ``infodict['fjac']``
+        and ``pcov`` there, one converged step before ``popt`` (``lm.py:468-473, 489``).
     return_pcov : ``"jtj"`` or ``"crlb"``: also return the ``[N, P, P]`` covariances (see :func:`covariance`).
     out : host path only: a ``BatchResult`` of preallocated C-contiguous arrays to write into (use
         :func:`pinned_empty` buffers, for the inputs too, so that the copies run asynchronously).
@@ -101,7 +103,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     one_d = model.model_id == models.MODEL_MULTI_EXP
     if _is_torch(data) and data.is_cuda:
         res = _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
-                          return_counts, group_lanes, timing)
+                          return_counts, group_lanes, timing, return_x_acc)
         if return_pcov:
             res = res._replace(pcov=covariance(model, res.popt, data.shape[1:], return_pcov, xdata))
         return res
@@ -127,11 +129,14 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         out = BatchResult(
             np.empty((n, n_param), np.float32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32),
             np.empty((n, n_param), np.float32) if return_stage1 else None, np.empty((n, 4), np.int32) if return_counts else None, None,
+            np.empty((n, n_param), np.float32) if return_x_acc else None,
         )
     else:
         want = [((n, n_param), np.float32), ((n,), np.int32), ((n,), np.int32), ((n,), np.float32),
                 ((n, n_param), np.float32) if return_stage1 else None, ((n, 4), np.int32) if return_counts else None]
-        out = BatchResult(*(tuple(out) + (None,) * (7 - len(out))))
+        out = BatchResult(*(tuple(out) + (None,) * (8 - len(out))))
+        if return_x_acc and out.x_acc is None:
+            out = out._replace(x_acc=np.empty((n, n_param), np.float32))
         for a, w in zip(out, want):
             if w is not None and (a is None or a.shape != w[0] or a.dtype != w[1] or not a.flags.c_contiguous):
                 raise ValueError("out: expected a C-contiguous %s array of shape %s" % (np.dtype(w[1]).name, w[0]))
@@ -144,6 +149,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         d.popt, d.info, d.nfev, d.chisq = (a[lo:hi].ctypes.data for a in tuple(out)[:4])
         d.p_ls = out.p_ls[lo:hi].ctypes.data if return_stage1 else None
         d.counts = out.counts[lo:hi].ctypes.data if return_counts else None
+        d.x_acc = out.x_acc[lo:hi].ctypes.data if return_x_acc else None
         return _lib.lib().dphlm_fit_batch_host(ctypes.byref(d), dev)
 
     if len(devices) == 1:
@@ -195,7 +201,7 @@ def pinned_empty(shape, dtype=np.float32):
 
 
 def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1, return_counts, group_lanes,
-                timing=False):
+                timing=False, return_x_acc=False):
     import torch
 
     if data.dtype != torch.float32 or not data.is_contiguous():
@@ -220,16 +226,18 @@ def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev,
     chisq = torch.empty(n, dtype=torch.float32, device=dev)
     p_ls = torch.empty((n, n_param), dtype=torch.float32, device=dev) if return_stage1 else None
     counts = torch.empty((n, 4), dtype=torch.int32, device=dev) if return_counts else None
+    x_acc = torch.empty((n, n_param), dtype=torch.float32, device=dev) if return_x_acc else None
     d = _fill_desc(model, method, n_param, dim0, dim1, n, ftol, xtol, gtol, maxfev, factor, group_lanes)
     d.data, d.p0, d.xaxis = data.data_ptr(), p0.data_ptr(), xa.data_ptr() if xa is not None else None
     d.popt, d.info, d.nfev, d.chisq = popt.data_ptr(), info.data_ptr(), nfev.data_ptr(), chisq.data_ptr()
     d.p_ls = p_ls.data_ptr() if return_stage1 else None
     d.counts = counts.data_ptr() if return_counts else None
+    d.x_acc = x_acc.data_ptr() if return_x_acc else None
     d.flags = _lib.FLAG_TIMING if timing else 0
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _check(_lib.lib().dphlm_fit_batch(ctypes.byref(d), ctypes.c_void_p(stream)))
-    return BatchResult(popt, info, nfev, chisq, p_ls, counts, None)
+    return BatchResult(popt, info, nfev, chisq, p_ls, counts, None, x_acc)
 
 
 def covariance(model, popt, shape, kind="jtj", xdata=None):
@@ -363,7 +371,7 @@ def curve_fit(f, xdata, ydata, p0=None, sigma=None, absolute_sigma=False, check_
     ftol, xtol, gtol = kwargs.get("ftol", FTOL), kwargs.get("xtol", XTOL), kwargs.get("gtol", 0.0)
     maxfev = kwargs.get("maxfev") or 100 * (p0.size + 1)
     res = curve_fit_batch(model, data, p0[None], method, xa, ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev,
-                          factor=kwargs.get("factor", 100.0))
+                          factor=kwargs.get("factor", 100.0), return_x_acc=True)
     info, popt = int(res.info[0]), res.popt[0].astype(float)
     fmt = dict(ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev)
     if info == -100:
@@ -371,9 +379,9 @@ def curve_fit(f, xdata, ydata, p0=None, sigma=None, absolute_sigma=False, check_
     if info < 0:  # the scipy pre-fit of the reference raises here (lm.py:642-644)
         raise RuntimeError("Optimal parameters not found: " + _MESSAGES.get(-info, "pre-fit failed (ier=%d)" % -info).format(**fmt))
     errmsg = _MESSAGES[info].format(**fmt)
-    # pcov = pinv(J^T J) from the SVD of the unweighted Jacobian (lm.py:672-677).  The reference uses J at the
-    # last accepted point; popt is at most one (converged, tiny) step away from it.
-    fjac = model.jac(xdata, *popt)
+    # pcov = pinv(J^T J) from the SVD of the unweighted Jacobian at the last ACCEPTED point, as in the reference
+    # (lm.py:672-677 with fjac from lm.py:468-473, 489)
+    fjac = model.jac(xdata, *res.x_acc[0].astype(float))
     _, s, vt = np.linalg.svd(fjac, full_matrices=False)
     keep = s > np.finfo(float).eps * max(fjac.shape) * s[0]
     s, vt = s[keep], vt[: keep.sum()]

@@ -51,6 +51,8 @@ typedef struct dphlm_desc {
     float* chisq;        /* [n_fits] chi-square at popt (0.5 sum r^2, or Poisson deviance / 2)          */
     float* p_ls;         /* optional [n_fits, n_param]: result of the least-squares pre-fit (lm.py:648) */
     int32_t* counts;     /* optional [n_fits, 4]: pre-fit evaluations, accepted, rejected steps, 0      */
+    float* x_acc;        /* optional [n_fits, n_param]: last ACCEPTED point of lm(); infodict['fjac'] and pcov of the
+                            reference are evaluated there, one step before popt                 (lm.py:468-473, 489) */
     float ftol, xtol, gtol, factor; /* lm()/leastsq keywords, forwarded to both stages (lm.py:643, 668) */
     int32_t maxfev;      /* <= 0: 100 * (n_param + 1)                                   (lm.py:306-307) */
     int32_t flags;       /* DPHLM_FLAG_* */

@@ -121,9 +121,10 @@ def test_single_fit_curve_fit_surface(golden):
         models.gauss2d, xy, y, g["p0"][0].astype(float), models.gauss2d_jac, "mle", full_output=True, return_stage1=True)
     assert info == ref_info
     np.testing.assert_allclose(popt, ref_popt, rtol=1e-4)
-    # pcov comes from J at popt here, from J at the last accepted point in the reference (one converged step apart)
+    # pcov and fjac come from J at the last accepted point, as in the reference
     scale = np.sqrt(np.outer(np.diag(ref_pcov), np.diag(ref_pcov)))
-    assert np.abs(pcov - ref_pcov).max() <= 1e-4 * scale.max() and np.abs((pcov - ref_pcov) / scale).max() < 1e-3
+    assert np.abs((pcov - ref_pcov) / scale).max() < 2e-5
+    np.testing.assert_allclose(infodict["fjac"], ref_infod["fjac"], rtol=1e-4, atol=1e-6)
     assert infodict["fvec"].shape == (225,) and infodict["fjac"].shape == (225, 5)
     with pytest.raises(RuntimeError, match="Optimal parameters not found"):
         dph.curve_fit(models.gauss2d, xy, y, g["p0"][0].astype(float), jac=models.gauss2d_jac, method="mle", maxfev=2)
@@ -282,7 +283,10 @@ def test_keywords_reach_both_stages_on_gpu(golden, kw):
     info, popt = r.info.cpu().numpy(), r.popt.cpu().numpy()
     ref = lm_oracle.fit_batch(models.gauss2d, g["data"][:n], g["p0"][:n], "mle", models.roi_grid(11, 11), **kw)
     conv_o, conv_r = (info >= 1) & (info <= 4), (ref["info"] >= 1) & (ref["info"] <= 4)
-    assert (conv_o == conv_r).mean() >= 0.98
+    # a tight maxfev cuts into the noise-limited last trips (nfev parity): a few fits that the reference finishes
+    # on its 11th trip finish on the 12th here, or vice versa
+    assert (conv_o == conv_r).mean() >= (0.95 if "maxfev" in kw else 0.98)
+    assert abs(int(conv_o.sum()) - int(conv_r.sum())) <= 3
     both = conv_o & conv_r
     assert (info[both] == ref["info"][both]).mean() >= 0.97
     rel = np.abs(popt[both][:, :4] - ref["popt"][both][:, :4]) / np.abs(ref["popt"][both][:, :4])
