@@ -98,6 +98,8 @@ DPH_HD float v_rcp(float a) { return f_rcp(a); }
 DPH_HD f2 v_rcp(f2 a) { return f2(f_rcp(a.x), f_rcp(a.y)); }
 DPH_HD float v_lg2(float a) { return f_lg2(a); }
 DPH_HD f2 v_lg2(f2 a) { return f2(f_lg2(a.x), f_lg2(a.y)); }
+DPH_HD float v_erf(float a) { return erff(a); }
+DPH_HD f2 v_erf(f2 a) { return f2(erff(a.x), erff(a.y)); }
 DPH_HD float v_max(float a, float b) { return fmaxf(a, b); }
 DPH_HD f2 v_max(f2 a, float b) { return f2(fmaxf(a.x, b), fmaxf(a.y, b)); }
 DPH_HD float v_min3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
@@ -348,6 +350,78 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         r = f_fma(ae * ga.v * vay, T(a.isy * s.d4), r);
         r = f_fma(ae * ga.u * ga.v, T((a.ay - a.ax) * s.d5), r);
         return r;
+    }
+};
+
+// Pixel-integrated symmetric Gaussian (erf model of a pixelated camera; SURVEY.md 8(f) rank 4, cf. upstream
+// notebooks/MLE_LevMarq_4Param_2013_11_12.m:44-46): amp * Ex(x) * Ey(y) + offset with
+// Ex = (erf((x - x0 + 1/2) a) - erf((x - x0 - 1/2) a)) / 2, a = 1 / (sqrt(2) sigma).  amp, x0, y0, sigma, offset.
+// It uses the GENERIC step difference any model with a Jacobian can use: for small steps
+// f(x + d) - f(x) = J(x + d/2) d + O(d^3) (midpoint rule; relative error ~ (d/scale)^2 / 24), for large steps the
+// direct difference; the switch sits where both have the same absolute error (~1e-7 f).
+struct Gauss2DIntegrated {
+    static constexpr int P = 5, NE = 1;
+    struct Par { float amp, x0, y0, sig, off, a, c, cs; };
+    struct Step { float d[5]; Par mid; bool direct; };
+    template <class T> struct Geo { T cx, cy, ex, ey, dex, dey, sex, sey; };
+    template <class T> struct Diff { T cx, cy; };
+    DPH_HD static void prepare(const float* p, Par& q) {
+        q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
+        const float is = f_rcp(q.sig);
+        q.a = 0.70710678118654752f * is;
+        q.c = 0.39894228040143268f * is;
+        q.cs = q.c * is;
+    }
+    // pixel integral of the unit-area Gaussian along one axis and its derivatives w.r.t. centre and sigma
+    template <class T> DPH_HD static void axis(const Par& q, T t, T& e, T& de, T& se) {
+        const T tp = t + T(0.5f), tm = t - T(0.5f);
+        const T zp = tp * T(q.a), zm = tm * T(q.a);
+        e = (v_erf(zp) - v_erf(zm)) * T(0.5f);
+        const T gp = v_ex2(zp * zp * T(-kLog2e)), gm = v_ex2(zm * zm * T(-kLog2e));
+        de = (gm - gp) * T(q.c);
+        se = (tm * gm - tp * gp) * T(q.cs);
+    }
+    template <class T> DPH_HD static void geometry(const Par& q, T cx, T cy, Geo<T>& g) {
+        g.cx = cx; g.cy = cy;
+        axis(q, cx - T(q.x0), g.ex, g.dex, g.sex);
+        axis(q, cy - T(q.y0), g.ey, g.dey, g.sey);
+    }
+    template <class T> DPH_HD static void expo(const Par&, const Geo<T>& g, T* e) { e[0] = g.ex * g.ey; }
+    template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
+    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
+        J[0] = e[0];
+        J[1] = g.dex * g.ey * T(q.amp);
+        J[2] = g.ex * g.dey * T(q.amp);
+        J[3] = f_fma(g.sex, g.ey, g.ex * g.sey) * T(q.amp);
+        J[4] = T(1.0f);
+    }
+    DPH_HD static void prepare_step(const Par& a, const Par&, const float* d, Step& s) {
+        float pm[5] = {a.amp + 0.5f * d[0], a.x0 + 0.5f * d[1], a.y0 + 0.5f * d[2], a.sig + 0.5f * d[3], a.off + 0.5f * d[4]};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s.d[k] = d[k];
+        prepare(pm, s.mid);
+        const float is = f_rcp(fabsf(a.sig));
+        const float rel = fmaxf(fmaxf(fabsf(d[0]) * f_rcp(fabsf(a.amp) + 1e-30f), fabsf(d[3]) * is), fmaxf(fabsf(d[1]), fabsf(d[2])) * is);
+        s.direct = !(rel <= 0.015625f);
+    }
+    template <class T> DPH_HD static void diff(const Par&, const Step&, const Geo<T>& g1, Diff<T>& df) { df.cx = g1.cx; df.cy = g1.cy; }
+    template <class T> DPH_HD static T jdot(const Par& q, const float* d, T cx, T cy) {  // J(q) . d at one pixel
+        Geo<T> g;
+        T e[1], J[P];
+        geometry(q, cx, cy, g);
+        expo(q, g, e);
+        jac(q, g, e, J);
+        T r = T(d[4]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r = f_fma(J[k], T(d[k]), r);
+        return r;
+    }
+    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
+        if (s.direct) return f_fma(T(a.amp + s.d[0]), eb[0], T(s.d[4])) - T(a.amp) * ea[0];
+        return jdot(s.mid, s.d, df.cx, df.cy);
+    }
+    template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& df, const T*) {
+        return jdot(a, s.d, df.cx, df.cy);
     }
 };
 

@@ -58,6 +58,9 @@ int validate_shape(const dphlm_desc* d) {
         case DPHLM_GAUSS2D_ELLIPTICAL:
             if (d->n_param != 7) return fail("gauss2d_elliptical takes 7 parameters");
             break;
+        case DPHLM_GAUSS2D_INTEGRATED:
+            if (d->n_param != 5) return fail("gauss2d_integrated takes 5 parameters");
+            break;
         case DPHLM_MULTI_EXP:
             if (d->n_param < 2 || d->n_param > 7) return fail("multi_exp supports 2..7 parameters (1-3 exponentials, optional offset)");
             if (!d->xaxis && d->n_fits > 0) return fail("multi_exp needs xaxis");
@@ -101,6 +104,7 @@ int launch_model(const dphlm_desc* d, int G, const KArgs& a, DeviceCtx* ctx, cud
     switch (d->model) {
         case DPHLM_GAUSS2D: return launch_gauss2d(G, mle, a, ctx, s);
         case DPHLM_GAUSS2D_ELLIPTICAL: return launch_gauss2d_elliptical(G, mle, a, ctx, s);
+        case DPHLM_GAUSS2D_INTEGRATED: return launch_gauss2d_integrated(G, mle, a, ctx, s);
         case DPHLM_MULTI_EXP:
             switch (d->n_param / 2) {
                 case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, ctx, s);
@@ -273,6 +277,7 @@ int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int ki
     switch (d->model) {
         case DPHLM_GAUSS2D: return launch_cov_gauss2d(a, s);
         case DPHLM_GAUSS2D_ELLIPTICAL: return launch_cov_gauss2d_elliptical(a, s);
+        case DPHLM_GAUSS2D_INTEGRATED: return launch_cov_gauss2d_integrated(a, s);
         case DPHLM_MULTI_EXP: return launch_cov_multi_exp(d->n_param, a, s);
     }
     return fail("unknown model id");

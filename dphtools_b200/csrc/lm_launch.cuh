@@ -482,11 +482,13 @@ int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
 // one per model family, defined in lm_inst_*.cu
 int launch_gauss2d(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
 int launch_gauss2d_elliptical(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
+int launch_gauss2d_integrated(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp1(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp2(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp3(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
 int launch_cov_gauss2d(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_elliptical(const CovArgs& a, cudaStream_t s);
+int launch_cov_gauss2d_integrated(const CovArgs& a, cudaStream_t s);
 int launch_cov_multi_exp(int n_param, const CovArgs& a, cudaStream_t s);
 
 #define DPH_DISPATCH_G(MO, G, mle, a, ctx, s)                                                      \

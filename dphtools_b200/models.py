@@ -13,6 +13,8 @@ Conventions:
 * 2-D models take ``xdata = np.stack([xx.ravel(), yy.ravel()])`` with ``xx`` the column index and
   ``yy`` the row index of a row-major ROI, integer pixel coordinates ``0..n-1``.
 * ``gauss2d``:  ``amp * exp(-((x-x0)^2 + (y-y0)^2) / (2 sigma^2)) + offset``
+* ``gauss2d_integrated``: ``amp * Ex(x) * Ey(y) + offset`` with ``Ex`` the integral of a unit-area Gaussian over the pixel
+  (erf model of a pixelated camera); ``amp`` is the photon count of the spot.
 * ``gauss2d_elliptical``: ``u =  c (x-x0) + s (y-y0)``, ``v = -s (x-x0) + c (y-y0)``,
   ``amp * exp(-(u^2/sigma_x^2 + v^2/sigma_y^2)/2) + offset`` with ``c, s = cos, sin(theta)``.
 """
@@ -23,6 +25,7 @@ import numpy as np
 MODEL_GAUSS2D = 0
 MODEL_GAUSS2D_ELLIPTICAL = 1
 MODEL_MULTI_EXP = 2
+MODEL_GAUSS2D_INTEGRATED = 3
 
 
 def gauss2d(xy, amp, x0, y0, sigma, offset):
@@ -78,6 +81,33 @@ def gauss2d_elliptical_jac(xy, amp, x0, y0, sigma_x, sigma_y, theta, offset):
     )
 
 
+def _pixel_integral(t, sigma):
+    """Integral of a unit-area 1-D Gaussian over the pixel [t - 1/2, t + 1/2] and its derivatives w.r.t. centre and sigma."""
+    from scipy.special import erf
+
+    a = 1.0 / (np.sqrt(2.0) * sigma)
+    tp, tm = t + 0.5, t - 0.5
+    e = 0.5 * (erf(tp * a) - erf(tm * a))
+    gp, gm = np.exp(-(tp * a) ** 2), np.exp(-(tm * a) ** 2)
+    c = 1.0 / (np.sqrt(2.0 * np.pi) * sigma)
+    return e, c * (gm - gp), c / sigma * (tm * gm - tp * gp)
+
+
+def gauss2d_integrated(xy, amp, x0, y0, sigma, offset):
+    """Pixel-integrated symmetric Gaussian: ``amp`` photons spread by a Gaussian of width ``sigma`` and integrated over
+    each unit pixel (erf model, cf. ``notebooks/MLE_LevMarq_4Param_2013_11_12.m:44-46`` upstream), plus ``offset``."""
+    ex, _, _ = _pixel_integral(xy[0] - x0, sigma)
+    ey, _, _ = _pixel_integral(xy[1] - y0, sigma)
+    return amp * ex * ey + offset
+
+
+def gauss2d_integrated_jac(xy, amp, x0, y0, sigma, offset):
+    """Jacobian of :func:`gauss2d_integrated`, shape ``(M, 5)``."""
+    ex, dex, sex = _pixel_integral(xy[0] - x0, sigma)
+    ey, dey, sey = _pixel_integral(xy[1] - y0, sigma)
+    return np.stack([ex * ey, amp * dex * ey, amp * ex * dey, amp * (sex * ey + ex * sey), np.ones_like(ex)], axis=1)
+
+
 def multi_exp(xdata, *args):
     r"""Sum of exponentials ``offset + sum_i a_i exp(-k_i x)`` (reference ``fitfuncs.py:20-34``)."""
     xdata = np.asarray(xdata, dtype=float)
@@ -111,8 +141,9 @@ def _tag(func, jac, model_id, n_param, name):
 _tag(gauss2d, gauss2d_jac, MODEL_GAUSS2D, 5, "gauss2d")
 _tag(gauss2d_elliptical, gauss2d_elliptical_jac, MODEL_GAUSS2D_ELLIPTICAL, 7, "gauss2d_elliptical")
 _tag(multi_exp, multi_exp_jac, MODEL_MULTI_EXP, None, "multi_exp")
+_tag(gauss2d_integrated, gauss2d_integrated_jac, MODEL_GAUSS2D_INTEGRATED, 5, "gauss2d_integrated")
 
-BUILTIN = {m.model_name: m for m in (gauss2d, gauss2d_elliptical, multi_exp)}
+BUILTIN = {m.model_name: m for m in (gauss2d, gauss2d_elliptical, multi_exp, gauss2d_integrated)}
 
 
 def roi_grid(height, width):

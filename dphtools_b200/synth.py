@@ -57,6 +57,21 @@ def gauss2d_rois(n, size=11, seed=0, photons=(100.0, 5000.0), sigma=(1.0, 1.6), 
     return dict(data=data, p0=gauss2d_p0(data), truth=truth, xaxis=None)
 
 
+def gauss2d_integrated_rois(n, size=11, seed=0, photons=(100.0, 5000.0), sigma=(1.0, 1.6), jitter=1.0, bg=(1.0, 10.0)):
+    """Pixel-integrated Gaussian spots; ``p0 = (sum(data - min), centre, centre, 1.3, max(min, 0.5))``."""
+    rng = np.random.default_rng(seed)
+    c = (size - 1) / 2
+    truth = np.stack(
+        [rng.uniform(*photons, n), c + rng.uniform(-jitter, jitter, n), c + rng.uniform(-jitter, jitter, n),
+         rng.uniform(*sigma, n), rng.uniform(*bg, n)], axis=1)
+    xy = models.roi_grid(size, size)
+    data = _poisson_rois(rng, models.gauss2d_integrated, xy, truth, (size, size))
+    p0 = gauss2d_p0(data)
+    flat = data.reshape(n, -1)
+    p0[:, 0] = np.maximum((flat - flat.min(1, keepdims=True)).sum(1), 1.0)
+    return dict(data=data, p0=p0, truth=truth, xaxis=None)
+
+
 def gauss2d_elliptical_p0(data):
     n, h, w = data.shape
     flat = data.reshape(n, -1)
@@ -137,4 +152,5 @@ WORKLOADS = {
     "c3_gauss2d_7": lambda n, seed=0: gauss2d_rois(n, 7, seed, jitter=0.75),
     "c4_ellip_15": lambda n, seed=0: gauss2d_elliptical_rois(n, 15, seed),
     "c5_multiexp_256": lambda n, seed=0: multi_exp_hists(n, 256, seed),
+    "c6_gauss2d_int_11": lambda n, seed=0: gauss2d_integrated_rois(n, 11, seed),
 }

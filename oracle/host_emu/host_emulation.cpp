@@ -153,6 +153,7 @@ extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, l
     } while (0)
     if (model == 0 && n_param == 5) RUN(Gauss2D);
     if (model == 1 && n_param == 7) RUN(Gauss2DElliptical);
+    if (model == 3 && n_param == 5) RUN(Gauss2DIntegrated);
     if (model == 2 && n_param == 2) RUN(MultiExp<1, false>);
     if (model == 2 && n_param == 3) RUN(MultiExp<1, true>);
     if (model == 2 && n_param == 4) RUN(MultiExp<2, false>);

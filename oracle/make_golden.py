@@ -39,8 +39,9 @@ SETS = {
     "c4_ls": ("c4_ellip_15", 2000, 14, "ls"),
     "c5_mle": ("c5_multiexp_256", 2000, 5, "mle"),
     "c5_ls": ("c5_multiexp_256", 2000, 15, "ls"),
+    "c6_mle": ("c6_gauss2d_int_11", 2000, 6, "mle"),
 }
-MODEL_OF = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp}
+MODEL_OF = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp, "c6": models.gauss2d_integrated}
 
 _G = {}
 

@@ -14,7 +14,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import dphtools_b200 as dph  # noqa: E402
 from dphtools_b200 import models, synth  # noqa: E402
 
-MODEL = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp}
+MODEL = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp,
+         "c6": models.gauss2d_integrated}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("workload")
