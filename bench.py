@@ -91,7 +91,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                     self.reasons |= {v for k, v in names.items() if r & k}
-                time.sleep(0.002)
+                time.sleep(0.005)
         except Exception as e:  # NVML missing: report that, never fail the run
             self.reasons.add("nvml_unavailable:" + type(e).__name__)
         self.ready.set()
@@ -136,8 +136,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--fits", type=int, default=N_FITS, help="fits per GPU and step")
     ap.add_argument("--group-lanes", type=int, default=0)
