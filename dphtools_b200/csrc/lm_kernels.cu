@@ -224,7 +224,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         }
     }
     int k = 0;
-    for (long long lo = 0; lo < d->n_fits && rc == 0; lo += chunk, k = (k + 1) % 3) {
+    for (long long lo = 0; lo < d->n_fits && rc == 0; lo += chunk, k = (k + 1) % kHostSlots) {
         const long long n = d->n_fits - lo < chunk ? d->n_fits - lo : chunk;
         auto& s = ctx->slots[k];
         char* b = s.buf;

@@ -370,6 +370,8 @@ int launch_cov(const CovArgs& a, cudaStream_t stream) {
     return 0;
 }
 
+constexpr int kHostSlots = 4;  // chunks in flight on the host path
+
 struct DeviceCtx {
     std::mutex mu;
     int sms = 0;
@@ -378,7 +380,7 @@ struct DeviceCtx {
         cudaStream_t stream = nullptr;
         char* buf = nullptr;
         size_t cap = 0;
-    } slots[3];
+    } slots[kHostSlots];
     // side stream for the follow-up launch of the pre-fit stragglers (forked from / joined into the caller's)
     // (a few, used round-robin, so that concurrent calls on different streams do not serialise behind each other)
     std::mutex fork_mu;
