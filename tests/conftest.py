@@ -15,6 +15,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_libraries():
+    """The shared libraries are build artefacts (git-ignored): build them when a fresh checkout runs the tests.
+    nvcc cross-compiles without a GPU; on the GPU box the prebuilt files travel with the snapshot."""
+    import shutil
+
+    from dphtools_b200 import build as cuda_build
+
+    if shutil.which(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+        cuda_build.build()
+    elif not os.path.exists(cuda_build.LIB):
+        pytest.exit("libdphlm.so is missing and nvcc is not available to build it", returncode=2)
+    from oracle import host_emu
+
+    host_emu.build()
+
+
 @pytest.fixture(scope="session")
 def golden():
     cache = {}
