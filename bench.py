@@ -90,9 +90,12 @@ class ClockSampler(threading.Thread):
                 nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             self.ready.set()
             while not self.stop_flag:
+                # query all the time (a freshly booted driver serves its first NVML queries slowly and stalls kernel
+                # launches meanwhile: those must have happened before the timed regions), record only when active
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 if self.active:
-                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.samples.append(mhz)
                     self.reasons |= {v for k, v in names.items() if r & k}
                 time.sleep(0.02)
         except Exception as e:  # NVML missing: report that, never fail the run
@@ -264,6 +267,7 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t_e2e.item())
+
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)

@@ -77,6 +77,8 @@ def lib():
 
 
 FLAG_TIMING = 1
+FLAG_NO_HANDOFF = 2
+FLAG_DATA_U16 = 4
 
 
 def last_kernel_ms():

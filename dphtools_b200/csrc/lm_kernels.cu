@@ -99,6 +99,19 @@ size_t workspace_bytes(const dphlm_desc* d) {
            (d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float));
 }
 
+__global__ void widen_u16(const unsigned short* __restrict__ in, float* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = float(in[i]);
+}
+
+int widen_async(const void* in, float* out, long long n, cudaStream_t s) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    widen_u16<<<(unsigned)blocks, 256, 0, s>>>(static_cast<const unsigned short*>(in), out, n);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+
 int launch_model(const dphlm_desc* d, int G, const KArgs& a, DeviceCtx* ctx, cudaStream_t s) {
     const bool mle = d->method == DPHLM_MLE;
     switch (d->model) {
@@ -135,8 +148,15 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     const size_t b_ier = ((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255);
     const size_t b_park = park_bytes(d->n_fits);
     const size_t b_pls = d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float);
+    const bool u16 = (d->flags & DPHLM_FLAG_DATA_U16) && !ws_in;  // the host path widens into its own slot buffer
+    const size_t b_wide = u16 ? (size_t)d->n_fits * a.h * a.w * sizeof(float) : 0;
     char* ws = ws_in;
-    if (!ws) CUDA_TRY(cudaMallocAsync(&ws, b_ier + b_park + b_pls, s));
+    if (!ws) CUDA_TRY(cudaMallocAsync(&ws, b_ier + b_park + ((b_pls + 255) & ~size_t(255)) + b_wide, s));
+    if (u16) {
+        float* wide = reinterpret_cast<float*>(ws + b_ier + b_park + ((b_pls + 255) & ~size_t(255)));
+        if (widen_async(d->data, wide, d->n_fits * a.h * a.w, s)) return -1;
+        a.data = wide;
+    }
     a.ier = reinterpret_cast<int*>(ws);
     if (!d->p_ls) a.p_ls = reinterpret_cast<float*>(ws + b_ier + b_park);
     // straggler lists (DPHLM_FLAG_NO_HANDOFF: keep every fit in the group that started it)
@@ -209,7 +229,9 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
                  b_cnt = align_up(chunk * 16), b_x = align_up(M * 4);
     const size_t b_ws = align_up(chunk * 4) + align_up(park_bytes(chunk)) + align_up(chunk * P * 4);
-    const size_t need = b_data + 4 * b_par + 3 * b_i + b_cnt + b_x + b_ws;
+    const bool u16 = d->flags & DPHLM_FLAG_DATA_U16;
+    const size_t b_raw = u16 ? align_up(chunk * M * 2) : 0;
+    const size_t need = b_data + b_raw + 4 * b_par + 3 * b_i + b_cnt + b_x + b_ws;
     int rc = 0;
     // one host call at a time per device: the staging slots are shared
     static std::mutex host_mu[64];
@@ -231,6 +253,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         dphlm_desc c = *d;
         c.n_fits = n;
         float* ddata = (float*)b; b += b_data;
+        char* draw = b; b += b_raw;
         float* dp0 = (float*)b; b += b_par;
         float* dpopt = (float*)b; b += b_par;
         float* dpls = (float*)b; b += b_par;
@@ -241,7 +264,12 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         int* dcnt = (int*)b; b += b_cnt;
         float* dx = (float*)b; b += b_x;
         char* dws = b;
-        CUDA_TRY(cudaMemcpyAsync(ddata, d->data + lo * M, n * M * 4, cudaMemcpyHostToDevice, s.stream));
+        if (u16) {
+            CUDA_TRY(cudaMemcpyAsync(draw, reinterpret_cast<const unsigned short*>(d->data) + lo * M, n * M * 2, cudaMemcpyHostToDevice, s.stream));
+            if (widen_async(draw, ddata, n * (long long)M, s.stream)) { rc = -1; break; }
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(ddata, d->data + lo * M, n * M * 4, cudaMemcpyHostToDevice, s.stream));
+        }
         CUDA_TRY(cudaMemcpyAsync(dp0, d->p0 + lo * P, n * P * 4, cudaMemcpyHostToDevice, s.stream));
         if (d->xaxis) CUDA_TRY(cudaMemcpyAsync(dx, d->xaxis, M * 4, cudaMemcpyHostToDevice, s.stream));
         c.data = ddata; c.p0 = dp0; c.xaxis = d->xaxis ? dx : nullptr;

@@ -44,7 +44,7 @@ typedef struct dphlm_desc {
     int32_t dim0, dim1;  /* ROI height, width; (n_bins, 1) for 1-D models */
     int32_t group_lanes; /* lanes of a warp that own one fit: 0 = automatic, else 4, 8, 16 or 32 */
     int64_t n_fits;
-    const float* data;   /* [n_fits, dim0, dim1] ydata, row-major                         (lm.py:512) */
+    const float* data;   /* [n_fits, dim0, dim1] ydata, row-major (uint16 with DPHLM_FLAG_DATA_U16)  (lm.py:512) */
     const float* xaxis;  /* MULTI_EXP: [dim0] shared xdata; NULL for 2-D models (pixel indices)        */
     const float* p0;     /* [n_fits, n_param] initial guesses                               (lm.py:514) */
     float* popt;         /* [n_fits, n_param] fitted parameters                             (lm.py:682) */
@@ -64,6 +64,9 @@ typedef struct dphlm_desc {
 #define DPHLM_FLAG_TIMING 1
 /* flags: do not hand stragglers (fits beyond ~p99.9 of the trip counts) to the warp-per-fit follow-up launches */
 #define DPHLM_FLAG_NO_HANDOFF 2
+/* flags: `data` points to uint16 camera counts instead of float32 (half the PCIe traffic on the host entry); they are
+ * widened on the device before the fit */
+#define DPHLM_FLAG_DATA_U16 4
 
 /* Fill the tolerances with the reference defaults (ftol = xtol = 1.49012e-8, gtol = 0, factor = 100,
  * maxfev = 0 -> 100 (P + 1); dphtools/utils/lm.py:228-233) and zero everything else. */

@@ -292,3 +292,12 @@ def test_keywords_reach_both_stages_on_gpu(golden, kw):
     rel = np.abs(popt[both][:, :4] - ref["popt"][both][:, :4]) / np.abs(ref["popt"][both][:, :4])
     assert np.quantile(rel.max(1), 0.99) < 1e-4
     assert (np.sign(info[~conv_o]) == np.sign(ref["info"][~conv_o])).all()
+
+
+def test_uint16_camera_counts_equal_float32(golden):
+    """Host entry with uint16 data (DPHLM_FLAG_DATA_U16): same answers as float32, half the bytes over PCIe."""
+    g = golden("c2_mle")
+    a = dph.curve_fit_batch(models.gauss2d, g["data"][:3000], g["p0"][:3000], "mle")
+    b = dph.curve_fit_batch(models.gauss2d, g["data"][:3000].astype(np.uint16), g["p0"][:3000], "mle")
+    np.testing.assert_array_equal(a.popt, b.popt)
+    np.testing.assert_array_equal(a.info, b.info)
