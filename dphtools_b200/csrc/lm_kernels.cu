@@ -90,9 +90,9 @@ int park_capacity(long long n) {
     if (c > 65536) c = 65536;
     return (int)c;
 }
-size_t park_bytes(long long n) {  // two stages: count, indices, records
-    const size_t cap = park_capacity(n);
-    return 256 + 2 * cap * sizeof(int) + 2 * cap * kParkRecord * sizeof(float);
+size_t park_ready_bytes(long long n) { return ((3 * (size_t)park_capacity(n) * sizeof(int)) + 255) & ~size_t(255); }
+size_t park_bytes(long long n) {  // header (sync words + work counters), three ready arrays, three record arrays
+    return 256 + park_ready_bytes(n) + 3 * (size_t)park_capacity(n) * kParkRecord * sizeof(float);
 }
 size_t workspace_bytes(const dphlm_desc* d) {
     return (((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255)) + park_bytes(d->n_fits) +
@@ -112,17 +112,17 @@ int widen_async(const void* in, float* out, long long n, cudaStream_t s) {
 }
 
 
-int launch_model(const dphlm_desc* d, int G, const KArgs& a, DeviceCtx* ctx, cudaStream_t s) {
+int launch_model(const dphlm_desc* d, int G, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s) {
     const bool mle = d->method == DPHLM_MLE;
     switch (d->model) {
-        case DPHLM_GAUSS2D: return launch_gauss2d(G, mle, a, ctx, s);
-        case DPHLM_GAUSS2D_ELLIPTICAL: return launch_gauss2d_elliptical(G, mle, a, ctx, s);
-        case DPHLM_GAUSS2D_INTEGRATED: return launch_gauss2d_integrated(G, mle, a, ctx, s);
+        case DPHLM_GAUSS2D: return launch_gauss2d(G, mle, a, pl, ctx, s);
+        case DPHLM_GAUSS2D_ELLIPTICAL: return launch_gauss2d_elliptical(G, mle, a, pl, ctx, s);
+        case DPHLM_GAUSS2D_INTEGRATED: return launch_gauss2d_integrated(G, mle, a, pl, ctx, s);
         case DPHLM_MULTI_EXP:
             switch (d->n_param / 2) {
-                case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, ctx, s);
-                case 2: return launch_multi_exp2(d->n_param & 1, G, mle, a, ctx, s);
-                case 3: return launch_multi_exp3(d->n_param & 1, G, mle, a, ctx, s);
+                case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, pl, ctx, s);
+                case 2: return launch_multi_exp2(d->n_param & 1, G, mle, a, pl, ctx, s);
+                case 3: return launch_multi_exp3(d->n_param & 1, G, mle, a, pl, ctx, s);
             }
     }
     return fail("unsupported model / n_param");
@@ -159,25 +159,26 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     }
     a.ier = reinterpret_cast<int*>(ws);
     if (!d->p_ls) a.p_ls = reinterpret_cast<float*>(ws + b_ier + b_park);
-    // straggler lists (DPHLM_FLAG_NO_HANDOFF: keep every fit in the group that started it)
-    a.park_cap = (d->flags & DPHLM_FLAG_NO_HANDOFF) ? 0 : park_capacity(d->n_fits);
-    // 256-byte header, zeroed once: the two park counters and the four work counters of the launches
-    a.park_count = reinterpret_cast<int*>(ws + b_ier);
+    // 256-byte header (sync words, then the work counters of the two main kernels at byte 64) and the straggler
+    // lists; DPHLM_FLAG_NO_HANDOFF keeps every fit in the group that started it
+    ParkLists pl{};
+    pl.cap = (d->flags & DPHLM_FLAG_NO_HANDOFF) ? 0 : park_capacity(d->n_fits);
+    pl.sync = reinterpret_cast<int*>(ws + b_ier);
     a.counter = reinterpret_cast<unsigned long long*>(ws + b_ier + 64);
-    a.park_idx = a.park_count + 64;
-    a.park_rec = reinterpret_cast<float*>(a.park_idx + 2 * (size_t)park_capacity(d->n_fits));
-    CUDA_TRY(cudaMemsetAsync(a.park_count, 0, 256, s));
+    pl.ready = reinterpret_cast<int*>(ws + b_ier + 256);
+    pl.rec = reinterpret_cast<float*>(ws + b_ier + 256 + park_ready_bytes(d->n_fits));
+    CUDA_TRY(cudaMemsetAsync(ws + b_ier, 0, 256 + (pl.cap ? park_ready_bytes(d->n_fits) : 0), s));
     int rc;
     {
         std::lock_guard<std::mutex> lk(ctx->fork_mu);  // the side stream and its events are shared per device
-        if (!ctx->sides[0].stream) {
+        if (!ctx->sides[0].stream_a) {
             for (auto& sd : ctx->sides) {
-                CUDA_TRY(cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking));
-                CUDA_TRY(cudaEventCreateWithFlags(&sd.fork_ev, cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&sd.join_ev, cudaEventDisableTiming));
+                CUDA_TRY(cudaStreamCreateWithFlags(&sd.stream_a, cudaStreamNonBlocking));
+                CUDA_TRY(cudaStreamCreateWithFlags(&sd.stream_b, cudaStreamNonBlocking));
+                for (cudaEvent_t* e : {&sd.fork_ev, &sd.mid_ev, &sd.join_a, &sd.join_b}) CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
             }
         }
-        rc = launch_model(d, G, a, ctx, s);
+        rc = launch_model(d, G, a, pl, ctx, s);
     }
     if (!ws_in) cudaFreeAsync(ws, s);
     return rc;

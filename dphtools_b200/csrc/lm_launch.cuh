@@ -30,12 +30,24 @@
 
 namespace dphlm {
 
+constexpr int kParkRecord = 32;  // floats per continuation record (>= 3 P + 6 for P <= 7)
+
 int fail(const std::string& m);  // sets the thread-local error text, returns -1
 #define CUDA_TRY(x)                                                                                    \
     do {                                                                                               \
         cudaError_t e_ = (x);                                                                          \
         if (e_ != cudaSuccess) return ::dphlm::fail(std::string(#x) + ": " + cudaGetErrorString(e_));  \
     } while (0)
+
+// One list of parked fits: producers append (atomic count, record, then the ready flag = fit + 1), consumers claim
+// with a CAS on `cons` once count > cons and wait for the flag.  Slots beyond `cap` do not exist.
+struct ParkQueue {
+    int* count;
+    int* cons;
+    int* ready;    // [cap], zero-initialised per call
+    float* rec;    // [cap][kParkRecord]
+    int cap;
+};
 
 struct KArgs {
     const float* data;
@@ -50,12 +62,15 @@ struct KArgs {
     int* counts;   // optional
     float* x_acc;  // optional: last accepted point of lm()
     unsigned long long* counter;
-    // straggler hand-off: fits that used up `budget` trips are parked here and resumed by a warp-per-fit launch
-    int* park_count;   // [1] number of parked fits of this stage (may exceed park_cap: the excess was not parked)
-    int* park_idx;     // [park_cap] fit indices
-    float* park_rec;   // [park_cap][kParkRecord] continuation records (Stage::save)
-    int park_cap;
-    int budget;        // trips before parking; <= 0: never
+    // straggler hand-off: a main kernel parks fits that used up `budget` trips in `produce`; a concurrently running
+    // poller kernel (one warp per fit) takes them from `consume[]` as they appear and finishes them
+    ParkQueue produce;      // where this kernel puts fits (cap == 0: nowhere)
+    ParkQueue consume[2];   // poller kernels: the queues they serve; consume[1] holds fits that START this stage here
+    int* wait_done[2];      // poller kernels: "producer has exited" flags of the kernels feeding consume[] (null: none)
+    int* exit_counter;      // CTAs of this kernel that have exited; the last one raises *done_flag
+    int* done_flag;
+    int* error_flag;        // raised if a poller gave up waiting (never in correct operation)
+    int budget;             // trips before parking; <= 0: never
     long long n_fits;
     int h, w;
     Options opt;
@@ -63,8 +78,8 @@ struct KArgs {
 };
 
 constexpr int kWarps = DPH_WARPS;
-constexpr int kParkRecord = 32;
-constexpr int kIerParked = -1;   // pre-fit exit code of a fit whose pre-fit is still running in the follow-up launch  // floats per continuation record (>= 3 P + 6 for P <= 7)
+constexpr int kIerParked = -1;   // pre-fit exit code of a fit whose pre-fit continues in the poller kernel
+constexpr long long kPollTimeoutCycles = 120000000000ll;  // ~60 s without work or news: a poller gives up (and says so)
 
 // per-fit stride of the shared-memory arrays: >= M and congruent to G modulo 32, so that the G-lane
 // groups of a warp touch disjoint banks
@@ -92,25 +107,32 @@ struct IoDevice {
     float* ynext;          // staging buffer [stride + kStageExtra] of this group
     long long next = -1;   // index of the staged fit, -1: nothing staged yet
 
-    __device__ int budget() const { return (RESUME || a.budget <= 0) ? 0x7fffffff : a.budget; }
+    __device__ int budget() const { return (RESUME || a.budget <= 0 || a.produce.cap <= 0) ? 0x7fffffff : a.budget; }
 
-    // hand a fit that has used up its trip budget to the warp-per-fit follow-up launch
+    // append a record to a queue: count, record, fence, ready flag (in this order)
+    __device__ static bool publish(const ParkQueue& q, const float* r, int nrec, long long fit) {
+        const int slot = atomicAdd(q.count, 1);
+        if (slot >= q.cap) return false;
+        for (int k = 0; k < nrec; ++k) q.rec[(size_t)slot * kParkRecord + k] = r[k];
+        __threadfence();
+        *reinterpret_cast<volatile int*>(q.ready + slot) = (int)fit + 1;
+        return true;
+    }
+
+    // hand a fit that has used up its trip budget to the poller kernel
     __device__ bool park(const Lanes<G>& ln, const Stage& st, long long fit) const {
         if (RESUME) return false;
         const int src = __ffs(ln.gmask) - 1;
-        int slot = 0;
-        if (ln.lane == 0) slot = atomicAdd(a.park_count, 1);
-        slot = __shfl_sync(ln.gmask, slot, src);
-        if (slot >= a.park_cap) return false;  // list full: the fit simply stays where it is
+        int ok = 0;
         if (ln.lane == 0) {
-            float r[kParkRecord];
-            st.save(r);
-#pragma unroll
-            for (int k = 0; k < Stage::kRecord; ++k) a.park_rec[(size_t)slot * kParkRecord + k] = r[k];
-            a.park_idx[slot] = (int)fit;
-            if (!MAIN) a.ier[fit] = kIerParked;  // the lm() kernel skips it; the follow-up launch runs it once its pre-fit is done
+            if (*reinterpret_cast<volatile int*>(a.produce.count) < a.produce.cap) {  // full list: the fit simply stays here
+                float r[kParkRecord];
+                st.save(r);
+                if (!MAIN) a.ier[fit] = kIerParked;  // the lm() kernel skips it; the lm() poller runs it once its pre-fit is done
+                ok = publish(a.produce, r, Stage::kRecord, fit) ? 1 : 0;  // on failure the fit stays here and store() rewrites ier
+            }
         }
-        return true;
+        return __shfl_sync(ln.gmask, ok, src) != 0;
     }
 
     // claim the next fit index for this group and start copying its inputs
@@ -129,70 +151,83 @@ struct IoDevice {
         if (MAIN && ln.lane == 0) cp_async4(ynext + stride + 7, a.ier + idx);
     }
 
-    // resume launch: next parked fit, loaded directly (a handful of fits, a whole warp each)
+    // poller kernel: wait for the next parked fit of the queues this kernel serves (one warp per fit).  Returns false
+    // when the queues are empty and every producer has exited.
     __device__ bool fetch_parked(const Lanes<G>& ln, PixelState<Mo::NE>& px, Stage& st, long long& fit) const {
-        const int src = __ffs(ln.gmask) - 1;
-        unsigned long long slot = 0;
-        if (ln.lane == 0) slot = atomicAdd(a.counter, 1ull);
-        slot = __shfl_sync(ln.gmask, slot, src);
-        int n_parked = *reinterpret_cast<volatile int*>(a.park_count);
-        if (n_parked > a.park_cap) n_parked = a.park_cap;
+        constexpr int P = Mo::P;
+        const long long t0 = clock64();
+        int q = -1, slot = 0;
         for (;;) {
-            bool fresh = false;
-            long long idx;
-            if ((long long)slot < n_parked) {
-                idx = a.park_idx[slot];
-            } else if (MAIN) {
-                // second list: fits whose PRE-FIT was parked; that has finished by now, start their lm() loop here
-                int n_late = *reinterpret_cast<volatile int*>(a.park_count - 1);
-                if (n_late > a.park_cap) n_late = a.park_cap;
-                const long long j = (long long)slot - n_parked;
-                if (j >= n_late) return false;
-                idx = (a.park_idx - a.park_cap)[j];
-                fresh = true;
-            } else {
+            // all lanes run the same loop; lane 0 decides
+            int claim = -1, got = 0, finished = 0;
+            if (ln.lane == 0) {
+                for (int k = 1; k >= 0 && claim < 0; --k) {  // fits waiting to START this stage first: they have the longest way to go
+                    const ParkQueue& pq = a.consume[k];
+                    if (pq.cap <= 0) continue;
+                    const int c = *reinterpret_cast<volatile int*>(pq.cons);
+                    int n = *reinterpret_cast<volatile int*>(pq.count);
+                    if (n > pq.cap) n = pq.cap;
+                    if (c < n && atomicCAS(pq.cons, c, c + 1) == c) { claim = k; got = c; }
+                }
+                if (claim < 0) {
+                    bool done = true;
+                    for (int k = 0; k < 2; ++k)
+                        if (a.wait_done[k] && *reinterpret_cast<volatile int*>(a.wait_done[k]) == 0) done = false;
+                    if (done) {  // producers are gone: whatever they published is visible now; look once more
+                        __threadfence();
+                        bool empty = true;
+                        for (int k = 0; k < 2; ++k) {
+                            const ParkQueue& pq = a.consume[k];
+                            if (pq.cap <= 0) continue;
+                            int n = *reinterpret_cast<volatile int*>(pq.count);
+                            if (n > pq.cap) n = pq.cap;
+                            if (*reinterpret_cast<volatile int*>(pq.cons) < n) empty = false;
+                        }
+                        finished = empty ? 1 : 0;
+                    }
+                    if (!finished && clock64() - t0 > kPollTimeoutCycles) {
+                        if (a.error_flag) *reinterpret_cast<volatile int*>(a.error_flag) = 1;
+                        finished = 1;
+                    }
+                }
+            }
+            claim = __shfl_sync(ln.gmask, claim, 0);
+            got = __shfl_sync(ln.gmask, got, 0);
+            finished = __shfl_sync(ln.gmask, finished, 0);
+            if (claim >= 0) { q = claim; slot = got; break; }
+            if (finished) return false;
+            __nanosleep(2000);
+        }
+        const ParkQueue& pq = a.consume[q];
+        int r = 0;
+        while ((r = *reinterpret_cast<volatile int*>(pq.ready + slot)) == 0) {  // the record is being written
+            if (clock64() - t0 > kPollTimeoutCycles) {
+                if (a.error_flag && ln.lane == 0) *reinterpret_cast<volatile int*>(a.error_flag) = 1;
                 return false;
             }
-            if (fresh) {
-                constexpr int P = Mo::P;
-                const int ier = -a.ier[idx] - 2;  // as stored by the resumed pre-fit
-                float pstart[P];
-#pragma unroll
-                for (int k = 0; k < P; ++k) pstart[k] = a.p_ls[idx * P + k];
-                if (ier < 1 || ier > 4) {
-                    if (ln.lane == 0) {
-#pragma unroll
-                        for (int k = 0; k < P; ++k) a.popt[idx * P + k] = pstart[k];
-                        a.info[idx] = ier == 0 ? -99 : -ier;
-                        a.nfev[idx] = 0;
-                        a.chisq[idx] = 0.0f;
-                        if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
-                        if (a.x_acc) {
-#pragma unroll
-                            for (int k = 0; k < P; ++k) a.x_acc[idx * P + k] = pstart[k];
-                        }
-                    }
-                    if (ln.lane == 0) slot = atomicAdd(a.counter, 1ull);
-                    slot = __shfl_sync(ln.gmask, slot, src);
-                    continue;
-                }
-                st.start(pstart);
-            }
-            const float* d = a.data + idx * px.M;
-            for (int i = ln.lane; i < px.M; i += G) {
-                float v = __ldg(d + i);
-                px.y[i] = (MAIN && MLE) ? clamp_nonneg(v) : v;
-            }
-            __syncwarp(ln.gmask);
-            if (!fresh) {
-                float r[kParkRecord];
-#pragma unroll
-                for (int k = 0; k < Stage::kRecord; ++k) r[k] = a.park_rec[(size_t)slot * kParkRecord + k];
-                st.resume(r);
-            }
-            fit = idx;
-            return true;
+            __nanosleep(200);
         }
+        __threadfence();
+        const long long idx = r - 1;
+        const float* d = a.data + idx * px.M;
+        for (int i = ln.lane; i < px.M; i += G) {
+            float v = __ldg(d + i);
+            px.y[i] = (MAIN && MLE) ? clamp_nonneg(v) : v;
+        }
+        __syncwarp(ln.gmask);
+        float rec[kParkRecord];
+        const volatile float* src = pq.rec + (size_t)slot * kParkRecord;
+        if (q == 1) {  // starts this stage here: the record is just the start parameters
+#pragma unroll
+            for (int k = 0; k < P; ++k) rec[k] = src[k];
+            st.start(rec);
+        } else {
+#pragma unroll
+            for (int k = 0; k < Stage::kRecord; ++k) rec[k] = src[k];
+            st.resume(rec);
+        }
+        fit = idx;
+        return true;
     }
 
     __device__ bool fetch(const Lanes<G>& ln, PixelState<Mo::NE>& px, Stage& st, long long& fit) {
@@ -251,9 +286,24 @@ struct IoDevice {
         if (ln.lane != 0) return;
 #pragma unroll
         for (int k = 0; k < Mo::P; ++k) a.p_ls[fit * Mo::P + k] = st.x[k];
-        // a resumed pre-fit ends while the lm() kernel may be reading this array: keep the entry <= kIerParked
-        a.ier[fit] = RESUME ? -st.ier - 2 : st.ier;
         if (a.counts) a.counts[4 * fit] = st.nfev;
+        if (!RESUME) { a.ier[fit] = st.ier; return; }
+        // a resumed pre-fit ends while the lm() kernel may be reading this array: keep the entry <= kIerParked ...
+        a.ier[fit] = -st.ier - 2;
+        if (st.ier >= 1 && st.ier <= 4) {  // ... and pass the fit on to the lm() poller, which starts its lm() loop
+            publish(a.produce, st.x, Mo::P, fit);
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < Mo::P; ++k) a.popt[fit * Mo::P + k] = st.x[k];  // the pre-fit failed: report it (scipy raises)
+        a.info[fit] = st.ier == 0 ? -99 : -st.ier;
+        a.nfev[fit] = 0;
+        a.chisq[fit] = 0.0f;
+        if (a.counts) { a.counts[4 * fit + 1] = 0; a.counts[4 * fit + 2] = 0; a.counts[4 * fit + 3] = 0; }
+        if (a.x_acc) {
+#pragma unroll
+            for (int k = 0; k < Mo::P; ++k) a.x_acc[fit * Mo::P + k] = st.x[k];
+        }
     }
     __device__ void store(const Lanes<G>& ln, const StageB<Mo, MLE>& st, long long fit) const {
         if (ln.lane != 0) return;
@@ -297,6 +347,16 @@ __global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(cons
     PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cx, cy, M, stride, 0};
     IO io{a, base + stride + kStageExtra};
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
+    if (a.exit_counter) {  // tell the pollers fed by this kernel when its last CTA has gone
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(a.exit_counter, 1) == (int)gridDim.x - 1) {
+                __threadfence();
+                *reinterpret_cast<volatile int*>(a.done_flag) = 1;
+            }
+        }
+    }
 }
 #endif
 
@@ -385,14 +445,14 @@ struct DeviceCtx {
     // (a few, used round-robin, so that concurrent calls on different streams do not serialise behind each other)
     std::mutex fork_mu;
     struct Side {
-        cudaStream_t stream = nullptr;
-        cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+        cudaStream_t stream_a = nullptr, stream_b = nullptr;
+        cudaEvent_t fork_ev = nullptr, mid_ev = nullptr, join_a = nullptr, join_b = nullptr;
     } sides[4];
     unsigned next_side = 0;
 };
 
 template <class Kern>
-int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream, long long work = -1) {
+int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream, int reserve = 0, int fixed_grid = 0) {
     KArgs a = a0;
     if (smem > 227 * 1024) return ::dphlm::fail("ROI too large for the shared-memory layout of this group size");
     // attribute setup and occupancy query once per (kernel instantiation, device, shared-memory size)
@@ -417,10 +477,11 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
         occ = c.occ;
     }
     // a.counter points into the call's own workspace header (zeroed once per call by fit_device)
-    long long grid = (long long)ctx->sms * occ;
-    if (work < 0) work = a.n_fits;
-    const long long need = (work + (long long)kWarps * fpw - 1) / ((long long)kWarps * fpw);
+    // main kernels fill the machine minus the CTA slots reserved for the concurrently running pollers
+    long long grid = (long long)ctx->sms * occ - reserve;
+    const long long need = (a.n_fits + (long long)kWarps * fpw - 1) / ((long long)kWarps * fpw);
     if (grid > need) grid = need;
+    if (fixed_grid > 0) grid = fixed_grid;
     if (grid < 1) grid = 1;
     kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -435,70 +496,118 @@ inline int budget_from_env(const char* name, int dflt) {  // tuning aid: DPHLM_B
     return e && atoi(e) > 0 ? atoi(e) : dflt;
 }
 
+// header words of the per-call workspace (zeroed once per call)
+enum { kSyncCountA = 0, kSyncCountB, kSyncCountL, kSyncConsA, kSyncConsB, kSyncConsL, kSyncDoneAMain, kSyncDoneAWide, kSyncDoneBMain,
+       kSyncExitAMain, kSyncExitAWide, kSyncExitBMain, kSyncError, kSyncWords = 16 };
+constexpr int kPollerCtas = 8;  // CTA slots kept free of main-kernel CTAs for each poller kernel (32 warps = 32 stragglers at a time)
+
+struct ParkLists {  // carved from the workspace by fit_device
+    int* sync;      // [kSyncWords]
+    int* ready;     // [3][cap]
+    float* rec;     // [3][cap][kParkRecord]
+    int cap;
+    __host__ ParkQueue queue(int which) const {  // 0: parked pre-fits, 1: parked lm() loops, 2: late pre-fits waiting for lm()
+        return ParkQueue{sync + kSyncCountA + which, sync + kSyncConsA + which, ready + (size_t)which * cap,
+                         rec + (size_t)which * cap * kParkRecord, cap};
+    }
+};
+
+// Both stages of curve_fit(method='ls'|'mle') for one batch.  Four kernels, two of them pollers:
+//   caller's stream : pre-fit main --------> lm() main ------------------> (join)
+//   side stream A   : pre-fit poller (parked pre-fits; passes each finished one on to the lm() poller)
+//   side stream B   :                        lm() poller (parked lm() loops + late pre-fits)
+// The pollers run concurrently with the main kernels, which leave kPollerCtas CTA slots free for each of them, so
+// every kernel is resident whatever order the hardware starts them in; a poller only ever waits for work or for the
+// "last CTA has exited" flag of the kernels that feed it, never the other way round.
 template <class Mo, bool MLE, int G>
-int launch(const KArgs& a0, DeviceCtx* ctx, cudaStream_t stream) {
+int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t stream) {
     const int M = a0.h * a0.w;
     constexpr int FPW = 32 / G;
     const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE));
     const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE));
-    const bool handoff = G < 32 && a0.park_cap > 0 && a0.budget >= 0;
+    const bool handoff = G < 32 && pl.cap > 0;
     using SA = StageA<Mo>;
     using SB = StageB<Mo, MLE>;
+    unsigned long long* const counters = a0.counter;  // work counters of the two main kernels
+    const ParkQueue none{nullptr, nullptr, nullptr, nullptr, 0};
     KArgs a = a0;
-    a.budget = handoff ? budget_from_env("DPHLM_BUDGET_A", kBudgetPrefit) : 0;
-    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[0], stream));
-    unsigned long long* const counters = a0.counter;  // four work counters, one per launch
     a.counter = counters;
-    int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream);
-    if (rc) return rc;
-    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
-    // The parked pre-fits (a handful of long ones) and the lm() kernel for everything else run concurrently.
-    // The straggler launch stays on the caller's stream, directly behind the pre-fit kernel, so that its few CTAs
-    // are resident before the persistent lm() kernel -- sent through the side stream -- takes every remaining slot.
+    a.produce = a.consume[0] = a.consume[1] = none;
+    a.wait_done[0] = a.wait_done[1] = nullptr;
+    a.exit_counter = a.done_flag = nullptr;
+    a.error_flag = pl.sync ? pl.sync + kSyncError : nullptr;
     KArgs b = a;
-    b.counter = counters + 2;
-    b.budget = handoff ? budget_from_env("DPHLM_BUDGET_B", kBudgetMain) : 0;
-    b.park_count += 1; b.park_idx += a.park_cap; b.park_rec += (size_t)a.park_cap * kParkRecord;
-    if (handoff) {
-        DeviceCtx::Side& sd = ctx->sides[ctx->next_side++ % 4];  // the caller holds ctx->fork_mu
-        CUDA_TRY(cudaEventRecord(sd.fork_ev, stream));
-        a.counter = counters + 1;
-        rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, a, 1, smem_w, ctx, stream, a.park_cap);
+    b.counter = counters + 1;
+    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[0], stream));
+    if (!handoff) {
+        a.budget = b.budget = 0;
+        int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream);
         if (rc) return rc;
-        CUDA_TRY(cudaStreamWaitEvent(sd.stream, sd.fork_ev, 0));
-        rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, sd.stream);
-        if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(sd.join_ev, sd.stream));
-        CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_ev, 0));
-        b.counter = counters + 3;
-        rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, b, 1, smem_w, ctx, stream, 2 * a.park_cap);
-        if (rc) return rc;
-    } else {
+        if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
         rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream);
         if (rc) return rc;
+        if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));
+        return 0;
     }
+    DeviceCtx::Side& sd = ctx->sides[ctx->next_side++ % 4];  // the caller holds ctx->fork_mu
+    // pre-fit main + its poller
+    a.budget = budget_from_env("DPHLM_BUDGET_A", kBudgetPrefit);
+    a.produce = pl.queue(0);
+    a.exit_counter = pl.sync + kSyncExitAMain; a.done_flag = pl.sync + kSyncDoneAMain;
+    KArgs aw = a;
+    aw.budget = 0;
+    aw.consume[0] = pl.queue(0); aw.produce = pl.queue(2);
+    aw.wait_done[0] = pl.sync + kSyncDoneAMain;
+    aw.exit_counter = pl.sync + kSyncExitAWide; aw.done_flag = pl.sync + kSyncDoneAWide;
+    CUDA_TRY(cudaEventRecord(sd.fork_ev, stream));
+    CUDA_TRY(cudaStreamWaitEvent(sd.stream_a, sd.fork_ev, 0));
+    int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream, kPollerCtas);
+    if (rc) return rc;
+    rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, aw, 1, smem_w, ctx, sd.stream_a, 0, kPollerCtas);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(sd.join_a, sd.stream_a));
+    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
+    // lm() main + its poller (both behind the pre-fit main kernel)
+    b.budget = budget_from_env("DPHLM_BUDGET_B", kBudgetMain);
+    b.produce = pl.queue(1);
+    b.exit_counter = pl.sync + kSyncExitBMain; b.done_flag = pl.sync + kSyncDoneBMain;
+    KArgs bw = b;
+    bw.budget = 0;
+    bw.produce = none;
+    bw.consume[0] = pl.queue(1); bw.consume[1] = pl.queue(2);
+    bw.wait_done[0] = pl.sync + kSyncDoneBMain; bw.wait_done[1] = pl.sync + kSyncDoneAWide;
+    bw.exit_counter = bw.done_flag = nullptr;
+    CUDA_TRY(cudaEventRecord(sd.mid_ev, stream));
+    CUDA_TRY(cudaStreamWaitEvent(sd.stream_b, sd.mid_ev, 0));
+    rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream, 2 * kPollerCtas);
+    if (rc) return rc;
+    rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, bw, 1, smem_w, ctx, sd.stream_b, 0, kPollerCtas);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(sd.join_b, sd.stream_b));
+    CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_a, 0));
+    CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_b, 0));
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));
     return 0;
 }
 
 // one per model family, defined in lm_inst_*.cu
-int launch_gauss2d(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
-int launch_gauss2d_elliptical(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
-int launch_gauss2d_integrated(int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
-int launch_multi_exp1(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
-int launch_multi_exp2(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
-int launch_multi_exp3(bool offset, int G, bool mle, const KArgs& a, DeviceCtx* ctx, cudaStream_t s);
+int launch_gauss2d(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_gauss2d_elliptical(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_gauss2d_integrated(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_multi_exp1(bool offset, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_multi_exp2(bool offset, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_multi_exp3(bool offset, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_cov_gauss2d(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_elliptical(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_integrated(const CovArgs& a, cudaStream_t s);
 int launch_cov_multi_exp(int n_param, const CovArgs& a, cudaStream_t s);
 
-#define DPH_DISPATCH_G(MO, G, mle, a, ctx, s)                                                      \
+#define DPH_DISPATCH_G(MO, G, mle, a, pl, ctx, s)                                                     \
     switch (G) {                                                                                   \
-        case 4: return (mle) ? launch<MO, true, 4>(a, ctx, s) : launch<MO, false, 4>(a, ctx, s);     \
-        case 8: return (mle) ? launch<MO, true, 8>(a, ctx, s) : launch<MO, false, 8>(a, ctx, s);     \
-        case 16: return (mle) ? launch<MO, true, 16>(a, ctx, s) : launch<MO, false, 16>(a, ctx, s);  \
-        case 32: return (mle) ? launch<MO, true, 32>(a, ctx, s) : launch<MO, false, 32>(a, ctx, s);  \
+        case 4: return (mle) ? launch<MO, true, 4>(a, pl, ctx, s) : launch<MO, false, 4>(a, pl, ctx, s);     \
+        case 8: return (mle) ? launch<MO, true, 8>(a, pl, ctx, s) : launch<MO, false, 8>(a, pl, ctx, s);     \
+        case 16: return (mle) ? launch<MO, true, 16>(a, pl, ctx, s) : launch<MO, false, 16>(a, pl, ctx, s);  \
+        case 32: return (mle) ? launch<MO, true, 32>(a, pl, ctx, s) : launch<MO, false, 32>(a, pl, ctx, s);  \
     }                                                                                              \
     return ::dphlm::fail("group_lanes must be 0, 4, 8, 16 or 32")
 
