@@ -499,7 +499,7 @@ inline int budget_from_env(const char* name, int dflt) {  // tuning aid: DPHLM_B
 // header words of the per-call workspace (zeroed once per call)
 enum { kSyncCountA = 0, kSyncCountB, kSyncCountL, kSyncConsA, kSyncConsB, kSyncConsL, kSyncDoneAMain, kSyncDoneAWide, kSyncDoneBMain,
        kSyncExitAMain, kSyncExitAWide, kSyncExitBMain, kSyncError, kSyncWords = 16 };
-constexpr int kPollerCtas = 8;  // CTA slots kept free of main-kernel CTAs for each poller kernel (32 warps = 32 stragglers at a time)
+constexpr int kPollerCtasDefault = 8;  // CTA slots kept free of main-kernel CTAs for each poller kernel (32 warps = 32 stragglers at a time)
 
 struct ParkLists {  // carved from the workspace by fit_device
     int* sync;      // [kSyncWords]
@@ -526,6 +526,7 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE));
     const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE));
     const bool handoff = G < 32 && pl.cap > 0;
+    const int kPollerCtas = budget_from_env("DPHLM_POLLER_CTAS", kPollerCtasDefault);  // tuning aid
     using SA = StageA<Mo>;
     using SB = StageB<Mo, MLE>;
     unsigned long long* const counters = a0.counter;  // work counters of the two main kernels
