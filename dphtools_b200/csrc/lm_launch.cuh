@@ -71,6 +71,7 @@ struct KArgs {
     int* done_flag;
     int* error_flag;        // raised if a poller gave up waiting (never in correct operation)
     int budget;             // trips before parking; <= 0: never
+    int max_backlog;        // parked fits waiting for a poller beyond which the main kernels stop parking
     long long n_fits;
     int h, w;
     Options opt;
@@ -125,7 +126,12 @@ struct IoDevice {
         const int src = __ffs(ln.gmask) - 1;
         int ok = 0;
         if (ln.lane == 0) {
-            if (*reinterpret_cast<volatile int*>(a.produce.count) < a.produce.cap) {  // full list: the fit simply stays here
+            // Park only while the pollers keep up: a backlog of more than a few fits per poller warp means the tail of this
+            // workload is heavier than the pollers' capacity, and then a straggler is better off staying in its group
+            // (which costs one group slot, as before the hand-off existed) than waiting in the list.
+            const int count = *reinterpret_cast<volatile int*>(a.produce.count);
+            const int backlog = count - *reinterpret_cast<volatile int*>(a.produce.cons);
+            if (count < a.produce.cap && backlog <= a.max_backlog) {
                 float r[kParkRecord];
                 st.save(r);
                 if (!MAIN) a.ier[fit] = kIerParked;  // the lm() kernel skips it; the lm() poller runs it once its pre-fit is done
@@ -553,6 +559,7 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     DeviceCtx::Side& sd = ctx->sides[ctx->next_side++ % 4];  // the caller holds ctx->fork_mu
     // pre-fit main + its poller
     a.budget = budget_from_env("DPHLM_BUDGET_A", kBudgetPrefit);
+    a.max_backlog = b.max_backlog = budget_from_env("DPHLM_MAX_BACKLOG", 3 * kPollerCtas * kWarps);
     a.produce = pl.queue(0);
     a.exit_counter = pl.sync + kSyncExitAMain; a.done_flag = pl.sync + kSyncDoneAMain;
     KArgs aw = a;
