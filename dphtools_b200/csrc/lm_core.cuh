@@ -222,7 +222,7 @@ DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
 // Pixel coordinates arrive as (cx, cy); 1-D models use cx only.
 
 struct Gauss2D {  // amp, x0, y0, sigma, offset
-    static constexpr int P = 5, NE = 1;
+    static constexpr int P = 5, NE = 1, kMinCtas = 3;
     struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3; };
     struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
     template <class T> struct Geo { T dx, dy, r2; };
@@ -270,7 +270,7 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
 };
 
 struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
-    static constexpr int P = 7, NE = 1;
+    static constexpr int P = 7, NE = 1, kMinCtas = 2;
     struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy; };
     struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day, t1, t2; };
     template <class T> struct Geo { T dx, dy, u, v; };
@@ -360,7 +360,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
 // f(x + d) - f(x) = J(x + d/2) d + O(d^3) (midpoint rule; relative error ~ (d/scale)^2 / 24), for large steps the
 // direct difference; the switch sits where both have the same absolute error (~1e-7 f).
 struct Gauss2DIntegrated {
-    static constexpr int P = 5, NE = 1;
+    static constexpr int P = 5, NE = 1, kMinCtas = 2;
     struct Par { float amp, x0, y0, sig, off, a, c, cs; };
     struct Step { float d[5]; Par mid; bool direct; };
     template <class T> struct Geo { T cx, cy, ex, ey, dex, dey, sex, sey; };
@@ -428,7 +428,7 @@ struct Gauss2DIntegrated {
 // sum of NEXP exponentials (+ offset): a0, k0, a1, k1, ..., [offset]   (fitfuncs.py:20-52)
 template <int NEXP, bool OFFSET>
 struct MultiExp {
-    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = NEXP;
+    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = NEXP, kMinCtas = NEXP >= 3 ? 2 : 3;
     struct Par { float a[NEXP], k[NEXP], off; };
     struct Step { float da[NEXP], dk[NEXP], doff; };
     template <class T> struct Geo { T x; };

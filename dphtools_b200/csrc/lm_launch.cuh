@@ -330,8 +330,14 @@ struct IoDevice {
 // words) and the double-buffered exponentials
 __host__ __device__ inline int group_region(int stride, int ne) { return 2 * (stride + kStageExtra) + 2 * ne * stride; }
 
+// CTAs per SM the register allocation is bounded for: 3 (<= 168 registers) where that costs no spills (the symmetric
+// Gaussian, single exponentials); models with more parameters or more per-pixel state declare kMinCtas = 2 (<= 255
+// registers): measured +28 % (mle) / +37 % (ls) for the 7-parameter elliptical Gaussian
+template <class Mo>
+constexpr int min_ctas() { return Mo::kMinCtas < DPH_MINB ? Mo::kMinCtas : DPH_MINB; }
+
 template <class Stage, class Mo, int G, class IO>
-__global__ void __launch_bounds__(kWarps * 32, DPH_MINB) dphlm_stage_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kernel(const KArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int FPW = 32 / G;  // fits in flight per warp
     const int M = a.h * a.w;
