@@ -280,6 +280,9 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         c.x_acc = d->x_acc ? dxacc : nullptr;
         rc = fit_device(&c, ctx, s.stream, dws);
         if (rc) break;
+        // the pollers' watchdog word (never set in correct operation) comes back with the results
+        if (!s.err_word) CUDA_TRY(cudaHostAlloc(&s.err_word, sizeof(int), cudaHostAllocDefault));
+        CUDA_TRY(cudaMemcpyAsync(s.err_word, reinterpret_cast<int*>(dws + align_up(n * 4)) + kSyncError, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->popt + lo * P, dpopt, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->info + lo, dinfo, n * 4, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->nfev + lo, dnfev, n * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -291,6 +294,8 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     for (auto& s : ctx->slots) {
         cudaError_t e = cudaStreamSynchronize(s.stream);
         if (e != cudaSuccess && rc == 0) rc = fail(std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+        if (s.err_word && *s.err_word && rc == 0) rc = fail("a straggler poller kernel gave up waiting (watchdog); results are incomplete");
+        if (s.err_word) *s.err_word = 0;
     }
     cudaSetDevice(prev);
     return rc;

@@ -452,6 +452,7 @@ struct DeviceCtx {
         cudaStream_t stream = nullptr;
         char* buf = nullptr;
         size_t cap = 0;
+        int* err_word = nullptr;  // pinned
     } slots[kHostSlots];
     // side stream for the follow-up launch of the pre-fit stragglers (forked from / joined into the caller's)
     // (a few, used round-robin, so that concurrent calls on different streams do not serialise behind each other)
