@@ -41,7 +41,8 @@ int get_ctx(int dev, DeviceCtx** out) {
 }
 
 int auto_group(int M) {
-    // measured on B200 (profiles/): 7x7 and 11x11 -> 4 lanes, 15x15 -> 8, 256 bins -> 16
+    // measured on B200 (profiles/): 7x7 -> 2 lanes, 11x11 -> 4, 15x15 -> 8, 256 bins -> 16
+    if (M <= 64) return 2;
     if (M <= 128) return 4;
     if (M <= 240) return 8;
     return 16;

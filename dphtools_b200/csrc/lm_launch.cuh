@@ -1,6 +1,6 @@
 // lm_launch.cuh -- kernel template and launcher shared by the per-model translation units.
 //
-// Execution model.  One fit is owned by a group of G lanes of a warp (G = 4, 8, 16 or 32, so a warp
+// Execution model.  One fit is owned by a group of G lanes of a warp (G = 2, 4, 8, 16 or 32, so a warp
 // carries 32/G fits).  Warps are persistent: each one pulls the next batch of 32/G consecutive fits from
 // a global atomic counter, stages their ROIs into its private slice of shared memory with coalesced
 // loads (clamping to >= 0 for the MLE estimator, lm.py:127, and checking finiteness, lm.py:651-652),
@@ -619,11 +619,12 @@ int launch_cov_multi_exp(int n_param, const CovArgs& a, cudaStream_t s);
 
 #define DPH_DISPATCH_G(MO, G, mle, a, pl, ctx, s)                                                     \
     switch (G) {                                                                                   \
+        case 2: return (mle) ? launch<MO, true, 2>(a, pl, ctx, s) : launch<MO, false, 2>(a, pl, ctx, s);     \
         case 4: return (mle) ? launch<MO, true, 4>(a, pl, ctx, s) : launch<MO, false, 4>(a, pl, ctx, s);     \
         case 8: return (mle) ? launch<MO, true, 8>(a, pl, ctx, s) : launch<MO, false, 8>(a, pl, ctx, s);     \
         case 16: return (mle) ? launch<MO, true, 16>(a, pl, ctx, s) : launch<MO, false, 16>(a, pl, ctx, s);  \
         case 32: return (mle) ? launch<MO, true, 32>(a, pl, ctx, s) : launch<MO, false, 32>(a, pl, ctx, s);  \
     }                                                                                              \
-    return ::dphlm::fail("group_lanes must be 0, 4, 8, 16 or 32")
+    return ::dphlm::fail("group_lanes must be 0, 2, 4, 8, 16 or 32")
 
 }  // namespace dphlm

@@ -42,7 +42,7 @@ typedef struct dphlm_desc {
     int32_t method;      /* enum dphlm_method */
     int32_t n_param;     /* 5 (GAUSS2D, GAUSS2D_INTEGRATED), 7 (ELLIPTICAL), 2..7 (MULTI_EXP: 2 per exponential, +1 = offset) */
     int32_t dim0, dim1;  /* ROI height, width; (n_bins, 1) for 1-D models */
-    int32_t group_lanes; /* lanes of a warp that own one fit: 0 = automatic, else 4, 8, 16 or 32 */
+    int32_t group_lanes; /* lanes of a warp that own one fit: 0 = automatic, else 2, 4, 8, 16 or 32 */
     int64_t n_fits;
     const float* data;   /* [n_fits, dim0, dim1] ydata, row-major (uint16 with DPHLM_FLAG_DATA_U16)  (lm.py:512) */
     const float* xaxis;  /* MULTI_EXP: [dim0] shared xdata; NULL for 2-D models (pixel indices)        */

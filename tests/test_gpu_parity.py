@@ -45,7 +45,7 @@ def test_cuda_matches_reference_goldens(golden, name, min_info, min_within):
     assert np.quantile(rel.max(1), 0.99) < 1e-4
 
 
-@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
 def test_every_group_size_gives_the_same_answers(golden, lanes):
     g = golden("c3_mle")
     out = _fit_gpu(g, group_lanes=lanes)
