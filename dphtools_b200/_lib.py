@@ -27,6 +27,7 @@ class Desc(ctypes.Structure):
         ("p_ls", ctypes.c_void_p), ("counts", ctypes.c_void_p), ("x_acc", ctypes.c_void_p),
         ("ftol", ctypes.c_float), ("xtol", ctypes.c_float), ("gtol", ctypes.c_float), ("factor", ctypes.c_float),
         ("maxfev", ctypes.c_int32), ("flags", ctypes.c_int32),
+        ("consts", ctypes.c_void_p),
     ]
 
 

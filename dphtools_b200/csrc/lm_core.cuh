@@ -227,6 +227,7 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
     template <class T> struct Geo { T dx, dy, r2; };
     template <class T> struct Diff { T dot, dr2, r20; };
+    DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
         float is = f_rcp(q.sig);
@@ -275,6 +276,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day, t1, t2; };
     template <class T> struct Geo { T dx, dy, u, v; };
     template <class T> struct Diff { T dx, dy, u, v; };
+    DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];
 #if defined(__CUDA_ARCH__)
@@ -359,18 +361,27 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
 // It uses the GENERIC step difference any model with a Jacobian can use: for small steps
 // f(x + d) - f(x) = J(x + d/2) d + O(d^3) (midpoint rule; relative error ~ (d/scale)^2 / 24), for large steps the
 // direct difference; the switch sits where both have the same absolute error (~1e-7 f).
-struct Gauss2DIntegrated {
-    static constexpr int P = 5, NE = 1, kMinCtas = 2;
-    struct Par { float amp, x0, y0, sig, off, a, c, cs; };
-    struct Step { float d[5]; Par mid; bool direct; };
+template <bool FIXED>
+struct Gauss2DIntegratedT {
+    static constexpr int P = FIXED ? 4 : 5, NE = 1, kMinCtas = 2, kOff = P - 1;
+    struct Par { float amp, x0, y0, sig = 1.0f, off, a = 0.70710678118654752f, c = 0.39894228040143268f, cs = 0.39894228040143268f; };
+    struct Step { float d[P]; Par mid; bool direct; };
     template <class T> struct Geo { T cx, cy, ex, ey, dex, dey, sex, sey; };
     template <class T> struct Diff { T cx, cy; };
-    DPH_HD static void prepare(const float* p, Par& q) {
-        q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
-        const float is = f_rcp(q.sig);
+    DPH_HD static void set_sigma(Par& q, float sig) {
+        q.sig = sig;
+        const float is = f_rcp(sig);
         q.a = 0.70710678118654752f * is;
         q.c = 0.39894228040143268f * is;
         q.cs = q.c * is;
+    }
+    // FIXED: the width is a constant of the call (consts[0]); prepare() leaves it alone
+    DPH_HD static void set_consts(Par& q, const float* consts) {
+        if (FIXED && consts) set_sigma(q, consts[0]);
+    }
+    DPH_HD static void prepare(const float* p, Par& q) {
+        q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.off = p[kOff];
+        if (!FIXED) set_sigma(q, p[3]);
     }
     // pixel integral of the unit-area Gaussian along one axis and its derivatives w.r.t. centre and sigma
     template <class T> DPH_HD static void axis(const Par& q, T t, T& e, T& de, T& se) {
@@ -392,16 +403,21 @@ struct Gauss2DIntegrated {
         J[0] = e[0];
         J[1] = g.dex * g.ey * T(q.amp);
         J[2] = g.ex * g.dey * T(q.amp);
-        J[3] = f_fma(g.sex, g.ey, g.ex * g.sey) * T(q.amp);
-        J[4] = T(1.0f);
+        if (!FIXED) J[3] = f_fma(g.sex, g.ey, g.ex * g.sey) * T(q.amp);
+        J[kOff] = T(1.0f);
     }
     DPH_HD static void prepare_step(const Par& a, const Par&, const float* d, Step& s) {
-        float pm[5] = {a.amp + 0.5f * d[0], a.x0 + 0.5f * d[1], a.y0 + 0.5f * d[2], a.sig + 0.5f * d[3], a.off + 0.5f * d[4]};
+        float pm[P];
+        pm[0] = a.amp + 0.5f * d[0]; pm[1] = a.x0 + 0.5f * d[1]; pm[2] = a.y0 + 0.5f * d[2];
+        if (!FIXED) pm[3] = a.sig + 0.5f * d[3];
+        pm[kOff] = a.off + 0.5f * d[kOff];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) s.d[k] = d[k];
+        for (int k = 0; k < P; ++k) s.d[k] = d[k];
+        s.mid = a;
         prepare(pm, s.mid);
         const float is = f_rcp(fabsf(a.sig));
-        const float rel = fmaxf(fmaxf(fabsf(d[0]) * f_rcp(fabsf(a.amp) + 1e-30f), fabsf(d[3]) * is), fmaxf(fabsf(d[1]), fabsf(d[2])) * is);
+        float rel = fmaxf(fabsf(d[0]) * f_rcp(fabsf(a.amp) + 1e-30f), fmaxf(fabsf(d[1]), fabsf(d[2])) * is);
+        if (!FIXED) rel = fmaxf(rel, fabsf(d[3]) * is);
         s.direct = !(rel <= 0.015625f);
     }
     template <class T> DPH_HD static void diff(const Par&, const Step&, const Geo<T>& g1, Diff<T>& df) { df.cx = g1.cx; df.cy = g1.cy; }
@@ -411,19 +427,21 @@ struct Gauss2DIntegrated {
         geometry(q, cx, cy, g);
         expo(q, g, e);
         jac(q, g, e, J);
-        T r = T(d[4]);
+        T r = T(d[kOff]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) r = f_fma(J[k], T(d[k]), r);
+        for (int k = 0; k < kOff; ++k) r = f_fma(J[k], T(d[k]), r);
         return r;
     }
     template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
-        if (s.direct) return f_fma(T(a.amp + s.d[0]), eb[0], T(s.d[4])) - T(a.amp) * ea[0];
+        if (s.direct) return f_fma(T(a.amp + s.d[0]), eb[0], T(s.d[kOff])) - T(a.amp) * ea[0];
         return jdot(s.mid, s.d, df.cx, df.cy);
     }
     template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& df, const T*) {
         return jdot(a, s.d, df.cx, df.cy);
     }
 };
+using Gauss2DIntegrated = Gauss2DIntegratedT<false>;       // (photons, x0, y0, sigma, offset)
+using Gauss2DIntegratedFixed = Gauss2DIntegratedT<true>;   // (photons, x0, y0, offset), sigma = consts[0]
 
 // sum of NEXP exponentials (+ offset): a0, k0, a1, k1, ..., [offset]   (fitfuncs.py:20-52)
 template <int NEXP, bool OFFSET>
@@ -433,6 +451,7 @@ struct MultiExp {
     struct Step { float da[NEXP], dk[NEXP], doff; };
     template <class T> struct Geo { T x; };
     template <class T> struct Diff { T x; };
+    DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) { q.a[i] = p[2 * i]; q.k[i] = p[2 * i + 1]; }
@@ -857,9 +876,11 @@ struct StageA {
     int ier, nfev;
     bool init, first, resumed;
 
-    DPH_HD void start(const float* p0) {
+    // `consts`: constants of the model for this call (Mo::set_consts), may be null
+    DPH_HD void start(const float* p0, const float* consts = nullptr) {
 #pragma unroll
         for (int i = 0; i < P; ++i) x[i] = p0[i];
+        Mo::set_consts(q0, consts);
         Mo::prepare(x, q0);
         par = delta = xnorm = pnorm = chi = 0.0f;
         ier = 0; nfev = 0;
@@ -875,11 +896,12 @@ struct StageA {
         r[2 * P] = chi; r[2 * P + 1] = par; r[2 * P + 2] = delta; r[2 * P + 3] = xnorm;
         r[2 * P + 4] = float(nfev); r[2 * P + 5] = first ? 1.0f : 0.0f;
     }
-    DPH_HD void resume(const float* r) {
+    DPH_HD void resume(const float* r, const float* consts = nullptr) {
 #pragma unroll
         for (int i = 0; i < P; ++i) { x[i] = r[i]; D[i] = r[P + i]; }
         chi = r[2 * P]; par = r[2 * P + 1]; delta = r[2 * P + 2]; xnorm = r[2 * P + 3];
         nfev = int(r[2 * P + 4]); first = r[2 * P + 5] != 0.0f;
+        Mo::set_consts(q0, consts);
         Mo::prepare(x, q0);
         pnorm = 0.0f; ier = 0;
         init = true; resumed = true;
@@ -1002,9 +1024,10 @@ struct StageB {
     int info, ev, n_acc, n_rej;
     bool init, live, resumed;
 
-    DPH_HD void start(const float* p_ls) {
+    DPH_HD void start(const float* p_ls, const float* consts = nullptr) {
 #pragma unroll
         for (int i = 0; i < P; ++i) x[i] = xret[i] = p_ls[i];
+        Mo::set_consts(q0, consts);
         Mo::prepare(x, q0);
         chisq_old = chisq_ret = lam = 0.0f;
         info = 5; ev = 0; n_acc = n_rej = 0;
@@ -1018,11 +1041,12 @@ struct StageB {
         r[3 * P] = chisq_old; r[3 * P + 1] = chisq_ret; r[3 * P + 2] = lam;
         r[3 * P + 3] = float(ev); r[3 * P + 4] = float(n_acc); r[3 * P + 5] = float(n_rej);
     }
-    DPH_HD void resume(const float* r) {
+    DPH_HD void resume(const float* r, const float* consts = nullptr) {
 #pragma unroll
         for (int i = 0; i < P; ++i) { x[i] = r[i]; dtd[i] = r[P + i]; xret[i] = r[2 * P + i]; }
         chisq_old = r[3 * P]; chisq_ret = r[3 * P + 1]; lam = r[3 * P + 2];
         ev = int(r[3 * P + 3]); n_acc = int(r[3 * P + 4]); n_rej = int(r[3 * P + 5]);
+        Mo::set_consts(q0, consts);
         Mo::prepare(x, q0);
         info = 5;
         init = true; live = false; resumed = true;
@@ -1173,6 +1197,7 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         float xn[P];
 #pragma unroll
         for (int i = 0; i < P; ++i) xn[i] = st.x[i] + p[i];
+        q1 = st.q0;  // carries the constants of the call (fixed-width model)
         Mo::prepare(xn, q1);
         Mo::prepare_step(st.q0, q1, p, step);
         const bool init = st.init, want_chi = Lanes<G>::warp_any(pass && st.wants_chi());

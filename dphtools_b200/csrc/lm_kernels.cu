@@ -40,6 +40,9 @@ int get_ctx(int dev, DeviceCtx** out) {
     return 0;
 }
 
+// number of floats `consts` holds for a model
+int model_consts(int model) { return model == DPHLM_GAUSS2D_INTEGRATED_FIXED ? 1 : 0; }
+
 int auto_group(int M) {
     // measured on B200 (profiles/): 7x7 -> 2 lanes, 11x11 -> 4, 15x15 -> 8, 256 bins -> 16
     if (M <= 64) return 2;
@@ -61,6 +64,10 @@ int validate_shape(const dphlm_desc* d) {
             break;
         case DPHLM_GAUSS2D_INTEGRATED:
             if (d->n_param != 5) return fail("gauss2d_integrated takes 5 parameters");
+            break;
+        case DPHLM_GAUSS2D_INTEGRATED_FIXED:
+            if (d->n_param != 4) return fail("gauss2d_integrated_fixed takes 4 parameters");
+            if (!d->consts && d->n_fits > 0) return fail("gauss2d_integrated_fixed needs consts[0] = sigma");
             break;
         case DPHLM_MULTI_EXP:
             if (d->n_param < 2 || d->n_param > 7) return fail("multi_exp supports 2..7 parameters (1-3 exponentials, optional offset)");
@@ -119,6 +126,7 @@ int launch_model(const dphlm_desc* d, int G, const KArgs& a, const ParkLists& pl
         case DPHLM_GAUSS2D: return launch_gauss2d(G, mle, a, pl, ctx, s);
         case DPHLM_GAUSS2D_ELLIPTICAL: return launch_gauss2d_elliptical(G, mle, a, pl, ctx, s);
         case DPHLM_GAUSS2D_INTEGRATED: return launch_gauss2d_integrated(G, mle, a, pl, ctx, s);
+        case DPHLM_GAUSS2D_INTEGRATED_FIXED: return launch_gauss2d_integrated_fixed(G, mle, a, pl, ctx, s);
         case DPHLM_MULTI_EXP:
             switch (d->n_param / 2) {
                 case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, pl, ctx, s);
@@ -133,7 +141,7 @@ int launch_model(const dphlm_desc* d, int G, const KArgs& a, const ParkLists& pl
 int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in = nullptr) {
     if (d->n_fits == 0) return 0;
     KArgs a{};
-    a.data = d->data; a.xaxis = d->xaxis; a.p0 = d->p0;
+    a.data = d->data; a.xaxis = d->xaxis; a.consts = d->consts; a.p0 = d->p0;
     a.popt = d->popt; a.info = d->info; a.nfev = d->nfev; a.chisq = d->chisq;
     a.p_ls = d->p_ls; a.counts = d->counts; a.x_acc = d->x_acc;
     a.n_fits = d->n_fits; a.h = d->dim0; a.w = d->dim1;
@@ -229,7 +237,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     if (chunk > 262144) chunk = 262144;
     if (const char* e = getenv("DPHLM_CHUNK")) { long long v = atoll(e); if (v > 0) chunk = v; }
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
-                 b_cnt = align_up(chunk * 16), b_x = align_up(M * 4);
+                 b_cnt = align_up(chunk * 16), b_x = align_up(M * 4) + 256;  // xaxis + model constants
     const size_t b_ws = align_up(chunk * 4) + align_up(park_bytes(chunk)) + align_up(chunk * P * 4);
     const bool u16 = d->flags & DPHLM_FLAG_DATA_U16;
     const size_t b_raw = u16 ? align_up(chunk * M * 2) : 0;
@@ -274,7 +282,10 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         }
         CUDA_TRY(cudaMemcpyAsync(dp0, d->p0 + lo * P, n * P * 4, cudaMemcpyHostToDevice, s.stream));
         if (d->xaxis) CUDA_TRY(cudaMemcpyAsync(dx, d->xaxis, M * 4, cudaMemcpyHostToDevice, s.stream));
-        c.data = ddata; c.p0 = dp0; c.xaxis = d->xaxis ? dx : nullptr;
+        float* dconsts = reinterpret_cast<float*>(reinterpret_cast<char*>(dx) + align_up(M * 4));
+        const int n_consts = model_consts(d->model);
+        if (n_consts) CUDA_TRY(cudaMemcpyAsync(dconsts, d->consts, n_consts * 4, cudaMemcpyHostToDevice, s.stream));
+        c.data = ddata; c.p0 = dp0; c.xaxis = d->xaxis ? dx : nullptr; c.consts = n_consts ? dconsts : nullptr;
         c.popt = dpopt; c.info = dinfo; c.nfev = dnfev; c.chisq = dchi;
         c.p_ls = dpls;  // always materialised in the slot buffer: the lm() kernel starts from it
         c.counts = d->counts ? dcnt : nullptr;
@@ -307,12 +318,13 @@ int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int ki
     if (kind != DPHLM_COV_JTJ && kind != DPHLM_COV_CRLB) return fail("kind must be DPHLM_COV_JTJ or DPHLM_COV_CRLB");
     if (d->n_fits > 0 && (!popt || !pcov)) return fail("null popt/pcov pointer");
     if (d->n_fits == 0) return 0;
-    CovArgs a{popt, d->xaxis, pcov, d->n_fits, d->dim0, d->dim1, kind};
+    CovArgs a{popt, d->xaxis, d->consts, pcov, d->n_fits, d->dim0, d->dim1, kind};
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (d->model) {
         case DPHLM_GAUSS2D: return launch_cov_gauss2d(a, s);
         case DPHLM_GAUSS2D_ELLIPTICAL: return launch_cov_gauss2d_elliptical(a, s);
         case DPHLM_GAUSS2D_INTEGRATED: return launch_cov_gauss2d_integrated(a, s);
+        case DPHLM_GAUSS2D_INTEGRATED_FIXED: return launch_cov_gauss2d_integrated_fixed(a, s);
         case DPHLM_MULTI_EXP: return launch_cov_multi_exp(d->n_param, a, s);
     }
     return fail("unknown model id");

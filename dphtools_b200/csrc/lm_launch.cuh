@@ -52,6 +52,7 @@ struct ParkQueue {
 struct KArgs {
     const float* data;
     const float* xaxis;
+    const float* consts;  // model constants of the call (Mo::set_consts), or null
     const float* p0;
     float* popt;
     int* info;
@@ -226,11 +227,11 @@ struct IoDevice {
         if (q == 1) {  // starts this stage here: the record is just the start parameters
 #pragma unroll
             for (int k = 0; k < P; ++k) rec[k] = src[k];
-            st.start(rec);
+            st.start(rec, a.consts);
         } else {
 #pragma unroll
             for (int k = 0; k < Stage::kRecord; ++k) rec[k] = src[k];
-            st.resume(rec);
+            st.resume(rec, a.consts);
         }
         fit = idx;
         return true;
@@ -273,13 +274,13 @@ struct IoDevice {
                     __syncwarp(ln.gmask);
                 }
                 fit = idx;
-                st.start(pstart);
+                st.start(pstart, a.consts);
                 return true;
             }
             bool bad = false;
             for (int i = ln.lane; i < px.M; i += G) bad |= !f_finite(px.y[i]);
             bad = __any_sync(ln.gmask, bad);
-            if (!bad) { fit = idx; st.start(pstart); return true; }
+            if (!bad) { fit = idx; st.start(pstart, a.consts); return true; }
             if (ln.lane == 0) {  // the reference raises ValueError (lm.py:651-652)
                 a.ier[idx] = 100;
 #pragma unroll
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
 struct CovArgs {
     const float* popt;
     const float* xaxis;
+    const float* consts;
     float* pcov;
     long long n_fits;
     int h, w, kind;
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(128) dphlm_cov_kernel(const CovArgs a) {
 #pragma unroll
     for (int k = 0; k < P; ++k) p[k] = active ? a.popt[fit * P + k] : 1.0f;
     typename Mo::Par q;
+    Mo::set_consts(q, a.consts);
     Mo::prepare(p, q);
     Acc<P, float> acc;
     acc.clear();
@@ -609,12 +612,14 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
 int launch_gauss2d(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_gauss2d_elliptical(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_gauss2d_integrated(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_gauss2d_integrated_fixed(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp1(bool offset, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp2(bool offset, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_multi_exp3(bool offset, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_cov_gauss2d(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_elliptical(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_integrated(const CovArgs& a, cudaStream_t s);
+int launch_cov_gauss2d_integrated_fixed(const CovArgs& a, cudaStream_t s);
 int launch_cov_multi_exp(int n_param, const CovArgs& a, cudaStream_t s);
 
 #define DPH_DISPATCH_G(MO, G, mle, a, pl, ctx, s)                                                     \

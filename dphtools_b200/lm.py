@@ -40,7 +40,8 @@ def _resolve_model(model):
     if getattr(model, "model_id", None) is None:
         raise NotImplementedError(
             "method='ls'|'mle' runs on the GPU and supports only the built-in models of dphtools_b200.models "
-            "(gauss2d, gauss2d_elliptical, multi_exp); there is no CPU fallback for arbitrary callables"
+            "(gauss2d, gauss2d_elliptical, gauss2d_integrated, gauss2d_integrated_fixed(sigma), multi_exp); there is no CPU "
+            "fallback for arbitrary callables"
         )
     return model
 
@@ -59,6 +60,26 @@ def _fill_desc(model, method, n_param, dim0, dim1, n_fits, ftol, xtol, gtol, max
     d.ftol, d.xtol, d.gtol, d.factor = ftol, xtol, gtol, factor
     d.maxfev = int(maxfev) if maxfev else 0
     return d
+
+
+def _consts_host(model):
+    """float32 array of the model's call constants (``dphlm_desc.consts``), or None."""
+    c = getattr(model, "consts", None)
+    return np.asarray(c, dtype=np.float32) if c else None
+
+
+def _consts_device(model, device):
+    """The same on ``device``, cached on the model so that repeated calls do not copy again."""
+    c = _consts_host(model)
+    if c is None:
+        return None
+    import torch
+
+    cache = model.__dict__.setdefault("_consts_dev", {})
+    key = str(device)
+    if key not in cache:
+        cache[key] = torch.as_tensor(c, device=device)
+    return cache[key]
 
 
 def shard_bounds(n, parts):
@@ -144,10 +165,13 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
                 raise ValueError("out: expected a C-contiguous %s array of shape %s" % (np.dtype(w[1]).name, w[0]))
     devices = [0] if device is None else ([device] if isinstance(device, int) else list(device))
 
+    consts = _consts_host(model)
+
     def run(dev, lo, hi):
         d = _fill_desc(model, method, n_param, dim0, dim1, hi - lo, ftol, xtol, gtol, maxfev, factor, group_lanes)
         d.data, d.p0 = data[lo:hi].ctypes.data, p0[lo:hi].ctypes.data
         d.xaxis = xa.ctypes.data if xa is not None else None
+        d.consts = consts.ctypes.data if consts is not None else None
         d.popt, d.info, d.nfev, d.chisq = (a[lo:hi].ctypes.data for a in tuple(out)[:4])
         d.p_ls = out.p_ls[lo:hi].ctypes.data if return_stage1 else None
         d.counts = out.counts[lo:hi].ctypes.data if return_counts else None
@@ -232,6 +256,8 @@ def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev,
     x_acc = torch.empty((n, n_param), dtype=torch.float32, device=dev) if return_x_acc else None
     d = _fill_desc(model, method, n_param, dim0, dim1, n, ftol, xtol, gtol, maxfev, factor, group_lanes)
     d.data, d.p0, d.xaxis = data.data_ptr(), p0.data_ptr(), xa.data_ptr() if xa is not None else None
+    consts = _consts_device(model, dev)
+    d.consts = consts.data_ptr() if consts is not None else None
     d.popt, d.info, d.nfev, d.chisq = popt.data_ptr(), info.data_ptr(), nfev.data_ptr(), chisq.data_ptr()
     d.p_ls = p_ls.data_ptr() if return_stage1 else None
     d.counts = counts.data_ptr() if return_counts else None
@@ -272,6 +298,8 @@ def covariance(model, popt, shape, kind="jtj", xdata=None):
             raise ValueError("multi_exp needs xdata")
         xa = torch.as_tensor(np.asarray(xdata, dtype=np.float32), device=pt.device).contiguous()
         d.xaxis = xa.data_ptr()
+    consts = _consts_device(model, pt.device)
+    d.consts = consts.data_ptr() if consts is not None else None
     pcov = torch.empty((n, n_param, n_param), dtype=torch.float32, device=pt.device)
     with torch.cuda.device(pt.device):
         stream = torch.cuda.current_stream(pt.device).cuda_stream

@@ -15,6 +15,8 @@ Conventions:
 * ``gauss2d``:  ``amp * exp(-((x-x0)^2 + (y-y0)^2) / (2 sigma^2)) + offset``
 * ``gauss2d_integrated``: ``amp * Ex(x) * Ey(y) + offset`` with ``Ex`` the integral of a unit-area Gaussian over the pixel
   (erf model of a pixelated camera); ``amp`` is the photon count of the spot.
+* ``gauss2d_integrated_fixed(sigma)``: factory for the 4-parameter ``(amp, x0, y0, offset)`` version with the width held
+  at ``sigma`` (the model of ``notebooks/MLE_LevMarq_4Param_2013_11_12.m`` upstream, whose PSF width is a call argument).
 * ``gauss2d_elliptical``: ``u =  c (x-x0) + s (y-y0)``, ``v = -s (x-x0) + c (y-y0)``,
   ``amp * exp(-(u^2/sigma_x^2 + v^2/sigma_y^2)/2) + offset`` with ``c, s = cos, sin(theta)``.
 """
@@ -26,6 +28,7 @@ MODEL_GAUSS2D = 0
 MODEL_GAUSS2D_ELLIPTICAL = 1
 MODEL_MULTI_EXP = 2
 MODEL_GAUSS2D_INTEGRATED = 3
+MODEL_GAUSS2D_INTEGRATED_FIXED = 4
 
 
 def gauss2d(xy, amp, x0, y0, sigma, offset):
@@ -108,6 +111,25 @@ def gauss2d_integrated_jac(xy, amp, x0, y0, sigma, offset):
     return np.stack([ex * ey, amp * dex * ey, amp * ex * dey, amp * (sex * ey + ex * sey), np.ones_like(ex)], axis=1)
 
 
+def gauss2d_integrated_fixed(sigma):
+    """Pixel-integrated Gaussian of FIXED width: returns the model ``f(xy, amp, x0, y0, offset)`` (with ``f.jac``), the
+    4-parameter fit of ``notebooks/MLE_LevMarq_4Param_2013_11_12.m:44-54`` upstream.  ``f.consts = (sigma,)`` travels to
+    the kernels as ``dphlm_desc.consts``."""
+    sigma = float(sigma)
+    if not sigma > 0:
+        raise ValueError("sigma must be positive")
+
+    def model(xy, amp, x0, y0, offset):
+        return gauss2d_integrated(xy, amp, x0, y0, sigma, offset)
+
+    def jac(xy, amp, x0, y0, offset):
+        return gauss2d_integrated_jac(xy, amp, x0, y0, sigma, offset)[:, [0, 1, 2, 4]]
+
+    _tag(model, jac, MODEL_GAUSS2D_INTEGRATED_FIXED, 4, "gauss2d_integrated_fixed")
+    model.consts = (sigma,)
+    return model
+
+
 def multi_exp(xdata, *args):
     r"""Sum of exponentials ``offset + sum_i a_i exp(-k_i x)`` (reference ``fitfuncs.py:20-34``)."""
     xdata = np.asarray(xdata, dtype=float)
@@ -144,6 +166,13 @@ _tag(multi_exp, multi_exp_jac, MODEL_MULTI_EXP, None, "multi_exp")
 _tag(gauss2d_integrated, gauss2d_integrated_jac, MODEL_GAUSS2D_INTEGRATED, 5, "gauss2d_integrated")
 
 BUILTIN = {m.model_name: m for m in (gauss2d, gauss2d_elliptical, multi_exp, gauss2d_integrated)}
+
+
+def resolve(name, consts=None):
+    """Model by name; ``gauss2d_integrated_fixed`` is built from ``consts = (sigma,)``."""
+    if name == "gauss2d_integrated_fixed":
+        return gauss2d_integrated_fixed(consts[0])
+    return BUILTIN[name]
 
 
 def roi_grid(height, width):

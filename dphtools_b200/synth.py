@@ -72,6 +72,14 @@ def gauss2d_integrated_rois(n, size=11, seed=0, photons=(100.0, 5000.0), sigma=(
     return dict(data=data, p0=p0, truth=truth, xaxis=None)
 
 
+def gauss2d_integrated_fixed_rois(n, size=11, seed=0, sigma=1.3):
+    """Pixel-integrated spots of one known width, fitted with the width held there: ``p0 = (photons, x0, y0, offset)``."""
+    sigma = float(np.float32(sigma))  # the constant reaches the kernels as a float32
+    w = gauss2d_integrated_rois(n, size, seed, sigma=(sigma, sigma))
+    keep = [0, 1, 2, 4]
+    return dict(data=w["data"], p0=np.ascontiguousarray(w["p0"][:, keep]), truth=w["truth"][:, keep], xaxis=None, consts=(sigma,))
+
+
 def gauss2d_elliptical_p0(data):
     n, h, w = data.shape
     flat = data.reshape(n, -1)
@@ -153,4 +161,5 @@ WORKLOADS = {
     "c4_ellip_15": lambda n, seed=0: gauss2d_elliptical_rois(n, 15, seed),
     "c5_multiexp_256": lambda n, seed=0: multi_exp_hists(n, 256, seed),
     "c6_gauss2d_int_11": lambda n, seed=0: gauss2d_integrated_rois(n, 11, seed),
+    "c7_gauss2d_intf_11": lambda n, seed=0: gauss2d_integrated_fixed_rois(n, 11, seed),
 }

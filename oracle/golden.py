@@ -12,5 +12,6 @@ def load_golden(name):
     g = {k: z[k] for k in z.files}
     g["data"] = g["data"].astype(np.float32)
     g["xaxis"] = g["xaxis"] if g["xaxis"].size else None
+    g["consts"] = g["consts"] if "consts" in g and g["consts"].size else None  # model constants (fixed-width Gaussian)
     g["workload"], _, _, g["method"], g["model"] = [str(s) for s in g["meta"]]
     return g

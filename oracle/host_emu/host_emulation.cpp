@@ -25,6 +25,7 @@ struct Buffers {
     int budget;  // trips after which a fit is parked and later resumed (exercises save/resume); 0 = never
     std::vector<Parked> parked;
     std::vector<char> was_parked;
+    const float* consts;  // model constants of the call, or null
 };
 
 template <class Mo>
@@ -48,7 +49,7 @@ struct HostIoPrefit {
                 if (resumed >= b.parked.size()) return false;
                 const Parked& pk = b.parked[resumed++];
                 for (int i = 0; i < b.M; ++i) px.y[i] = b.data[pk.fit * b.M + i];
-                st.resume(pk.rec.data());
+                st.resume(pk.rec.data(), b.consts);
                 fit = pk.fit;
                 return true;
             }
@@ -56,7 +57,7 @@ struct HostIoPrefit {
             bool bad = false;
             for (int i = 0; i < b.M; ++i) { float v = b.data[idx * b.M + i]; bad |= !std::isfinite(v); px.y[i] = v; }
             for (int k = 0; k < Mo::P; ++k) pstart[k] = b.p0[idx * Mo::P + k];
-            if (!bad) { fit = idx; st.start(pstart); return true; }
+            if (!bad) { fit = idx; st.start(pstart, b.consts); return true; }
             b.ier[idx] = 100;
             for (int k = 0; k < Mo::P; ++k) b.p_ls[idx * Mo::P + k] = pstart[k];
             for (int k = 0; k < 4; ++k) b.counts[4 * idx + k] = 0;
@@ -90,7 +91,7 @@ struct HostIoMain {
                 if (resumed >= b.parked.size()) return false;
                 const Parked& pk = b.parked[resumed++];
                 for (int i = 0; i < b.M; ++i) { float v = b.data[pk.fit * b.M + i]; px.y[i] = MLE ? clamp_nonneg(v) : v; }
-                st.resume(pk.rec.data());
+                st.resume(pk.rec.data(), b.consts);
                 fit = pk.fit;
                 return true;
             }
@@ -100,7 +101,7 @@ struct HostIoMain {
             if (ier >= 1 && ier <= 4) {
                 for (int i = 0; i < b.M; ++i) { float v = b.data[idx * b.M + i]; px.y[i] = MLE ? clamp_nonneg(v) : v; }
                 fit = idx;
-                st.start(pstart);
+                st.start(pstart, b.consts);
                 return true;
             }
             for (int k = 0; k < Mo::P; ++k) b.popt[idx * Mo::P + k] = pstart[k];
@@ -142,9 +143,10 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
 
 extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, long n, const float* data,
                              const float* xaxis, const float* p0, float ftol, float xtol, float gtol, float factor,
-                             int maxfev, int budget, float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts) {
+                             int maxfev, int budget, float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts,
+                             const float* consts) {
     Options opt{ftol, xtol, gtol, factor, maxfev};
-    Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0), budget, {}, std::vector<char>(n, 0)};
+    Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0), budget, {}, std::vector<char>(n, 0), consts};
 #define RUN(...)                                                 \
     do {                                                         \
         if (method) run<__VA_ARGS__, true>(h, w, xaxis, opt, b);  \
@@ -154,6 +156,7 @@ extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, l
     if (model == 0 && n_param == 5) RUN(Gauss2D);
     if (model == 1 && n_param == 7) RUN(Gauss2DElliptical);
     if (model == 3 && n_param == 5) RUN(Gauss2DIntegrated);
+    if (model == 4 && n_param == 4 && consts) RUN(Gauss2DIntegratedFixed);
     if (model == 2 && n_param == 2) RUN(MultiExp<1, false>);
     if (model == 2 && n_param == 3) RUN(MultiExp<1, true>);
     if (model == 2 && n_param == 4) RUN(MultiExp<2, false>);

@@ -40,14 +40,16 @@ SETS = {
     "c5_mle": ("c5_multiexp_256", 2000, 5, "mle"),
     "c5_ls": ("c5_multiexp_256", 2000, 15, "ls"),
     "c6_mle": ("c6_gauss2d_int_11", 2000, 6, "mle"),
+    "c7_mle": ("c7_gauss2d_intf_11", 2000, 7, "mle"),
 }
-MODEL_OF = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp, "c6": models.gauss2d_integrated}
+MODEL_OF = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp, "c6": models.gauss2d_integrated,
+            "c7": models.gauss2d_integrated_fixed(1.3)}
 
 _G = {}
 
 
-def _init(model_name, method, xdata):
-    _G.update(model=models.BUILTIN[model_name], method=method, xdata=xdata)
+def _init(model_name, method, xdata, consts):
+    _G.update(model=models.resolve(model_name, consts), method=method, xdata=xdata)
 
 
 def _one(args):
@@ -72,8 +74,9 @@ def _one(args):
 
 def make(name):
     workload, n, seed, method = SETS[name]
-    model = MODEL_OF[name[:2]]
     w = synth.WORKLOADS[workload](n, seed)
+    consts = w.get("consts")
+    model = models.resolve(MODEL_OF[name[:2]].model_name, consts)
     data, p0 = w["data"], w["p0"]
     if w["xaxis"] is not None:
         xdata = w["xaxis"].astype(np.float64)
@@ -81,7 +84,7 @@ def make(name):
         xdata = models.roi_grid(*data.shape[1:])
     flat = data.reshape(n, -1).astype(np.float64)
     t0 = time.time()
-    with Pool(os.cpu_count(), initializer=_init, initargs=(model.model_name, method, xdata)) as pool:
+    with Pool(os.cpu_count(), initializer=_init, initargs=(model.model_name, method, xdata, consts)) as pool:
         res = pool.map(_one, zip(flat, p0.astype(np.float64)), chunksize=64)
     dt = time.time() - t0
     p_ls = np.stack([r[0] for r in res])
@@ -94,6 +97,7 @@ def make(name):
         out, data=data.astype(np.uint16), p0=p0, p_ls=p_ls, popt=popt, info=info, nfev=nfev,
         truth=w["truth"], xaxis=np.zeros(0, np.float32) if w["xaxis"] is None else w["xaxis"],
         meta=np.array([workload, str(n), str(seed), method, model.model_name]),
+        consts=np.asarray(consts if consts else [], np.float32),
     )
     vals, cnt = np.unique(info, return_counts=True)
     print(f"{name}: {n} fits in {dt:.1f}s ({n / dt:.0f} fits/s on {os.cpu_count()} procs)  info={dict(zip(vals.tolist(), cnt.tolist()))}"

@@ -6,7 +6,7 @@ import pytest
 from dphtools_b200 import models
 from oracle import lm_oracle
 
-SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle"]
+SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle", "c7_mle"]
 
 
 def _xdata(g):
@@ -22,7 +22,7 @@ def test_oracle_matches_reference_goldens(golden, name):
     # always include the hard cases the reference produced (non-info-1 exits, long trajectories)
     hard = np.flatnonzero((g["info"] != 1) | (g["nfev"] > 25))[:50]
     idx = np.union1d(np.arange(n), hard)
-    model = models.BUILTIN[g["model"]]
+    model = models.resolve(g["model"], g["consts"])
     out = lm_oracle.fit_batch(model, g["data"][idx], g["p0"][idx], g["method"], _xdata(g))
     np.testing.assert_array_equal(out["info"], g["info"][idx])
     np.testing.assert_array_equal(out["nfev"], g["nfev"][idx])
@@ -51,6 +51,7 @@ def test_oracle_curve_fit_surface(golden):
     (models.gauss2d, (50.0, 5.3, 4.6, 1.4, 3.0)),
     (models.gauss2d_elliptical, (50.0, 7.3, 6.6, 1.4, 2.1, 0.3, 3.0)),
     (models.gauss2d_integrated, (1500.0, 7.3, 6.6, 1.4, 3.0)),
+    (models.gauss2d_integrated_fixed(1.25), (1500.0, 7.3, 6.6, 3.0)),
     (models.multi_exp, (900.0, 2.2, 300.0, 0.4, 4.0)),
     (models.multi_exp, (900.0, 2.2, 300.0, 0.4)),
 ])
