@@ -107,3 +107,17 @@ def test_multi_exp_fit_driver_reproduces_the_reference_tests_and_guesses():
     g = fitfuncs.guess_multi_exp(y, t, 2, offset=True)
     assert g.shape == (5,) and g[1] > g[3] > 0 and g[0] > 0 and g[2] > 0
     assert fitfuncs.guess_multi_exp(y, t, 2, offset=False).shape == (4,)
+
+
+def test_integration_stub_mirrors_the_descriptor_layout():
+    """The ctypes structure shown to a dphtools maintainer in INTEGRATION.md has the fields and offsets of dphlm_desc."""
+    text = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    m = re.search(r'class _Desc\(ctypes\.Structure\):[^\n]*\n(    _fields_ = .*?\("consts", ctypes\.c_void_p\)\])', text, re.S)
+    assert m, "stub not found"
+    ns = {"ctypes": ctypes}
+    exec("class _Desc(ctypes.Structure):\n" + m.group(1), ns)
+    stub = ns["_Desc"]
+    assert [f[0] for f in stub._fields_] == [f[0] for f in _lib.Desc._fields_]
+    assert ctypes.sizeof(stub) == ctypes.sizeof(_lib.Desc)
+    for name, _ in stub._fields_:
+        assert getattr(stub, name).offset == getattr(_lib.Desc, name).offset, name
