@@ -176,7 +176,9 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     a.counter = reinterpret_cast<unsigned long long*>(ws + b_ier + 64);
     pl.ready = reinterpret_cast<int*>(ws + b_ier + 256);
     pl.rec = reinterpret_cast<float*>(ws + b_ier + 256 + park_ready_bytes(d->n_fits));
-    CUDA_TRY(cudaMemsetAsync(ws + b_ier, 0, 256 + (pl.cap ? park_ready_bytes(d->n_fits) : 0), s));
+    // the pre-fit results start as "not published yet" (exit code 0, parameters NaN) for an lm() kernel that starts early
+    CUDA_TRY(cudaMemsetAsync(a.p_ls, 0xFF, (size_t)d->n_fits * d->n_param * sizeof(float), s));
+    CUDA_TRY(cudaMemsetAsync(ws, 0, b_ier + 256 + (pl.cap ? park_ready_bytes(d->n_fits) : 0), s));
     int rc;
     {
         std::lock_guard<std::mutex> lk(ctx->fork_mu);  // the side stream and its events are shared per device

@@ -101,6 +101,14 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// release / acquire on a word another kernel of the same call polls
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 constexpr int kStageExtra = 8;  // floats after the staged ROI: start parameters (<= 7) and one int
 
 template <class Stage, class Mo, int G, bool MAIN, bool MLE, bool RESUME>
@@ -135,8 +143,10 @@ struct IoDevice {
             if (count < a.produce.cap && backlog <= a.max_backlog) {
                 float r[kParkRecord];
                 st.save(r);
-                if (!MAIN) a.ier[fit] = kIerParked;  // the lm() kernel skips it; the lm() poller runs it once its pre-fit is done
-                ok = publish(a.produce, r, Stage::kRecord, fit) ? 1 : 0;  // on failure the fit stays here and store() rewrites ier
+                ok = publish(a.produce, r, Stage::kRecord, fit) ? 1 : 0;  // on failure the fit stays here
+                // the lm() kernel skips a parked pre-fit (the lm() poller runs it once its pre-fit is done); written only after
+                // the hand-off succeeded because the lm() kernel may already be reading this array (early start, see launch())
+                if (!MAIN && ok) *reinterpret_cast<volatile int*>(a.ier + fit) = kIerParked;
             }
         }
         return __shfl_sync(ln.gmask, ok, src) != 0;
@@ -243,7 +253,13 @@ struct IoDevice {
         float pstart[P];
         if (next < 0) stage(ln, px.M, px.stride);
         for (;;) {
-            if (next >= a.n_fits) return false;
+            if (next >= a.n_fits) {
+                // No new fits are left, only the ones in flight: from here on a kernel launched behind this one with the
+                // programmatic-serialization attribute (the lm() kernel behind the pre-fit kernel) may take the CTA slots
+                // this grid frees while it drains.  No effect on ordinary launches.
+                if (!MAIN) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                return false;
+            }
             const long long idx = next;
             cp_async_wait_all();
             __syncwarp(ln.gmask);
@@ -252,13 +268,32 @@ struct IoDevice {
 #pragma unroll
             for (int k = 0; k < P; ++k) pstart[k] = px.y[px.stride + k];
             if (MAIN) {
-                const int ier = __float_as_int(px.y[px.stride + 7]);
+                int ier = __float_as_int(px.y[px.stride + 7]);
+                // This kernel is launched so that it may start while the pre-fit kernel is still draining (programmatic
+                // dependent launch).  The pre-fit publishes the parameters of a fit, then its exit code (release); both arrays
+                // start the call as "not yet" (exit code 0, parameters NaN), so a staged copy made too early shows.
+                bool early = ier == 0;
+#pragma unroll
+                for (int k = 0; k < P; ++k) early |= pstart[k] != pstart[k];
+                if (early) {
+                    const long long t0 = clock64();
+                    while ((ier = ld_acquire(a.ier + idx)) == 0) {
+                        if (clock64() - t0 > kPollTimeoutCycles) {  // never in correct operation: report instead of hanging
+                            if (a.error_flag) *reinterpret_cast<volatile int*>(a.error_flag) = 1;
+                            ier = 99;
+                            break;
+                        }
+                        __nanosleep(200);
+                    }
+#pragma unroll
+                    for (int k = 0; k < P; ++k) pstart[k] = __ldcg(a.p_ls + idx * P + k);
+                }
                 if (ier <= kIerParked) continue;  // pre-fit parked: still running (or just finished) in the follow-up launch, which will also run lm()
                 if (ier < 1 || ier > 4) {  // the pre-fit failed: report it, do not fit (scipy raises, lm.py:642-644)
                     if (ln.lane == 0) {
 #pragma unroll
                         for (int k = 0; k < P; ++k) a.popt[idx * P + k] = pstart[k];
-                        a.info[idx] = ier == 0 ? -99 : -ier;
+                        a.info[idx] = -ier;
                         a.nfev[idx] = 0;
                         a.chisq[idx] = 0.0f;
                         if (a.counts) { a.counts[4 * idx + 1] = 0; a.counts[4 * idx + 2] = 0; a.counts[4 * idx + 3] = 0; }
@@ -282,10 +317,10 @@ struct IoDevice {
             bad = __any_sync(ln.gmask, bad);
             if (!bad) { fit = idx; st.start(pstart, a.consts); return true; }
             if (ln.lane == 0) {  // the reference raises ValueError (lm.py:651-652)
-                a.ier[idx] = 100;
 #pragma unroll
                 for (int k = 0; k < P; ++k) a.p_ls[idx * P + k] = pstart[k];
                 if (a.counts) reinterpret_cast<int4*>(a.counts)[idx] = make_int4(0, 0, 0, 0);
+                st_release(a.ier + idx, 100);
             }
         }
     }
@@ -294,16 +329,17 @@ struct IoDevice {
 #pragma unroll
         for (int k = 0; k < Mo::P; ++k) a.p_ls[fit * Mo::P + k] = st.x[k];
         if (a.counts) a.counts[4 * fit] = st.nfev;
-        if (!RESUME) { a.ier[fit] = st.ier; return; }
+        const int ier = st.ier == 0 ? 99 : st.ier;  // 0 is "not published yet" to the lm() kernel
+        if (!RESUME) { st_release(a.ier + fit, ier); return; }
         // a resumed pre-fit ends while the lm() kernel may be reading this array: keep the entry <= kIerParked ...
-        a.ier[fit] = -st.ier - 2;
+        *reinterpret_cast<volatile int*>(a.ier + fit) = -ier - 2;
         if (st.ier >= 1 && st.ier <= 4) {  // ... and pass the fit on to the lm() poller, which starts its lm() loop
             publish(a.produce, st.x, Mo::P, fit);
             return;
         }
 #pragma unroll
         for (int k = 0; k < Mo::P; ++k) a.popt[fit * Mo::P + k] = st.x[k];  // the pre-fit failed: report it (scipy raises)
-        a.info[fit] = st.ier == 0 ? -99 : -st.ier;
+        a.info[fit] = -ier;
         a.nfev[fit] = 0;
         a.chisq[fit] = 0.0f;
         if (a.counts) { a.counts[4 * fit + 1] = 0; a.counts[4 * fit + 2] = 0; a.counts[4 * fit + 3] = 0; }
@@ -468,7 +504,8 @@ struct DeviceCtx {
 };
 
 template <class Kern>
-int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream, int reserve = 0, int fixed_grid = 0) {
+int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ctx, cudaStream_t stream, int reserve = 0, int fixed_grid = 0,
+                 bool early_start = false) {
     KArgs a = a0;
     if (smem > 227 * 1024) return ::dphlm::fail("ROI too large for the shared-memory layout of this group size");
     // attribute setup and occupancy query once per (kernel instantiation, device, shared-memory size)
@@ -499,6 +536,16 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
     if (grid > need) grid = need;
     if (fixed_grid > 0) grid = fixed_grid;
     if (grid < 1) grid = 1;
+    if (early_start) {  // may begin while the previous kernel of the stream drains; it synchronises per fit, not per grid
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+        return 0;
+    }
     kern<<<(unsigned)grid, kWarps * 32, smem, stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -579,7 +626,8 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     aw.exit_counter = pl.sync + kSyncExitAWide; aw.done_flag = pl.sync + kSyncDoneAWide;
     CUDA_TRY(cudaEventRecord(sd.fork_ev, stream));
     CUDA_TRY(cudaStreamWaitEvent(sd.stream_a, sd.fork_ev, 0));
-    int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream, kPollerCtas);
+    CUDA_TRY(cudaStreamWaitEvent(sd.stream_b, sd.fork_ev, 0));
+    int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream, 2 * kPollerCtas);
     if (rc) return rc;
     rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, aw, 1, smem_w, ctx, sd.stream_a, 0, kPollerCtas);
     if (rc) return rc;
@@ -595,9 +643,11 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     bw.consume[0] = pl.queue(1); bw.consume[1] = pl.queue(2);
     bw.wait_done[0] = pl.sync + kSyncDoneBMain; bw.wait_done[1] = pl.sync + kSyncDoneAWide;
     bw.exit_counter = bw.done_flag = nullptr;
-    CUDA_TRY(cudaEventRecord(sd.mid_ev, stream));
-    CUDA_TRY(cudaStreamWaitEvent(sd.stream_b, sd.mid_ev, 0));
-    rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream, 2 * kPollerCtas);
+    // The lm() kernel directly follows the pre-fit kernel in the stream and may start in the CTA slots that one frees while its
+    // last fits finish: it waits per fit for the pre-fit's exit code (IoDevice::fetch), not for the grid.  Timing events
+    // between the two launches would serialise them, so a timed call keeps the plain stream order.
+    const bool early = !a.ev && !getenv("DPHLM_NO_EARLY_START");
+    rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream, 2 * kPollerCtas, 0, early);
     if (rc) return rc;
     rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, bw, 1, smem_w, ctx, sd.stream_b, 0, kPollerCtas);
     if (rc) return rc;
