@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <algorithm>
 #include <mutex>
+#include <vector>
 #include <string>
 
 #include "../../include/dphlm.h"
@@ -232,12 +234,24 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     DeviceCtx* ctx;
     if (get_ctx(device, &ctx)) return -1;
     const size_t M = (size_t)d->dim0 * d->dim1, P = d->n_param;
-    // chunking: about 4 chunks in flight over 3 streams so that copies overlap kernels and the tail of one
-    // chunk's kernel overlaps the head of the next; DPHLM_CHUNK overrides (tuning)
-    long long chunk = (d->n_fits + 3) / 4;
-    if (chunk < 16384) chunk = 16384;
-    if (chunk > 262144) chunk = 262144;
-    if (const char* e = getenv("DPHLM_CHUNK")) { long long v = atoll(e); if (v > 0) chunk = v; }
+    // Chunking: the copies of one chunk overlap the kernels of the others (one stream per chunk, kHostSlots in flight).  The
+    // kernels cannot start before the first chunk has landed and need longer per fit than the copy does, so the chunks
+    // grow: n/10, 2n/10, 3n/10, 4n/10 for a batch up to ~6e5 fits, then the cap.  DPHLM_CHUNK = fixed size (tuning).
+    const long long kChunkMin = 8192, kChunkMax = 262144;
+    long long step = d->n_fits / 10;
+    if (step < kChunkMin) step = kChunkMin;
+    if (step > kChunkMax) step = kChunkMax;
+    long long fixed = 0;
+    if (const char* e = getenv("DPHLM_CHUNK")) { long long v = atoll(e); if (v > 0) fixed = v; }
+    std::vector<long long> bounds{0};
+    for (long long c = fixed ? fixed : step; bounds.back() < d->n_fits;) {
+        long long hi = bounds.back() + c;
+        if (hi > d->n_fits || d->n_fits - hi < kChunkMin / 2) hi = d->n_fits;  // no crumb at the end
+        bounds.push_back(hi);
+        if (!fixed && c + step <= kChunkMax) c += step;
+    }
+    long long chunk = 0;  // the largest one sizes the slot buffers
+    for (size_t i = 1; i < bounds.size(); ++i) chunk = std::max(chunk, bounds[i] - bounds[i - 1]);
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
                  b_cnt = align_up(chunk * 16), b_x = align_up(M * 4) + 256;  // xaxis + model constants
     const size_t b_ws = align_up(chunk * 4) + align_up(park_bytes(chunk)) + align_up(chunk * P * 4);
@@ -258,8 +272,8 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         }
     }
     int k = 0;
-    for (long long lo = 0; lo < d->n_fits && rc == 0; lo += chunk, k = (k + 1) % kHostSlots) {
-        const long long n = d->n_fits - lo < chunk ? d->n_fits - lo : chunk;
+    for (size_t ci = 0; ci + 1 < bounds.size() && rc == 0; ++ci, k = (k + 1) % kHostSlots) {
+        const long long lo = bounds[ci], n = bounds[ci + 1] - lo;
         auto& s = ctx->slots[k];
         char* b = s.buf;
         dphlm_desc c = *d;
