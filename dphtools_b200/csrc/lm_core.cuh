@@ -109,6 +109,12 @@ DPH_HD float v_sel_small(float a, float thr, float x, float y) { return fabsf(a)
 DPH_HD f2 v_sel_small(f2 a, float thr, f2 x, f2 y) { return f2(fabsf(a.x) <= thr ? x.x : y.x, fabsf(a.y) <= thr ? x.y : y.y); }
 DPH_HD float v_pick(bool c, float x, float y) { return c ? x : y; }
 DPH_HD f2 v_pick(bool c, f2 x, f2 y) { return f2(c ? x.x : y.x, c ? x.y : y.y); }
+DPH_HD float v_gather(const float* t, float i) { return t[int(i)]; }  // table lookup by (integer-valued) index
+DPH_HD f2 v_gather(const float* t, f2 i) { return f2(t[int(i.x)], t[int(i.y)]); }
+DPH_HD float v_clamp(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
+DPH_HD f2 v_clamp(f2 a, float lo, float hi) { return f2(fminf(fmaxf(a.x, lo), hi), fminf(fmaxf(a.y, lo), hi)); }
+DPH_HD float v_nonneg01(float a) { return a >= 0.0f ? 1.0f : 0.0f; }  // 1 where a >= 0, else 0
+DPH_HD f2 v_nonneg01(f2 a) { return f2(a.x >= 0.0f ? 1.0f : 0.0f, a.y >= 0.0f ? 1.0f : 0.0f); }
 DPH_HD float v_hsum(float a) { return a; }
 DPH_HD float v_hsum(f2 a) { return a.x + a.y; }
 DPH_HD float v_hmin(float a) { return a; }
@@ -227,6 +233,8 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
     template <class T> struct Geo { T dx, dy, r2; };
     template <class T> struct Diff { T dot, dr2, r20; };
+    static constexpr int kTable = 0;
+    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
@@ -276,6 +284,8 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day, t1, t2; };
     template <class T> struct Geo { T dx, dy, u, v; };
     template <class T> struct Diff { T dx, dy, u, v; };
+    static constexpr int kTable = 0;
+    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];
@@ -376,6 +386,8 @@ struct Gauss2DIntegratedT {
         q.cs = q.c * is;
     }
     // FIXED: the width is a constant of the call (consts[0]); prepare() leaves it alone
+    static constexpr int kTable = 0;
+    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
     DPH_HD static void set_consts(Par& q, const float* consts) {
         if (FIXED && consts) set_sigma(q, consts[0]);
     }
@@ -451,6 +463,8 @@ struct MultiExp {
     struct Step { float da[NEXP], dk[NEXP], doff; };
     template <class T> struct Geo { T x; };
     template <class T> struct Diff { T x; };
+    static constexpr int kTable = 0;
+    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
 #pragma unroll
@@ -497,6 +511,123 @@ struct MultiExp {
     }
 };
 
+// Sum of NEXP exponentials convolved with an instrument response function (IRF) sampled on the histogram's own uniform
+// grid (own formulation, not derived from the GPL supplement in the upstream notebooks):
+//   f_j = offset + sum_i a_i C_i[j],   C_i[j] = sum_{q=0}^{min(j-m0, W-1)} irf[q] exp(-k_i (j - m0 - q) dt)   (0 for j < m0)
+// with the W IRF taps starting at bin m0.  Parameters as MultiExp: a0, k0, a1, k1, ..., [offset].
+// consts = [W, m0, dt, irf[0..W-1]].  With u = (j - m0) dt and e = exp(-k u):
+//   C = e S[w],  D = -dC/dk = u C - e T[w],   w = min(j - m0, W-1),
+//   S[w] = sum_{q<=w} irf[q] exp(k q dt),  T[w] = sum_{q<=w} irf[q] q dt exp(k q dt)
+// so one exponential per bin and two prefix-sum tables per exponential and trial point (fill_tables: a shuffle scan over
+// the lanes of the group, in the group's shared memory).  C and D are the per-bin values stored between trips (NE = 2 NEXP),
+// which makes J(x) d at the accepted point free, and f(x+d) - f(x) uses dC = -dk (D_a + D_b)/2 (trapezoid rule on dC/dk,
+// relative error (dk u)^2 / 12) for small dk u and the direct difference otherwise.
+constexpr int kIrfTaps = 32;
+template <int NEXP, bool OFFSET>
+struct MultiExpIrf {
+    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = 2 * NEXP, kMinCtas = 2;
+    static constexpr int kTable = 2 * NEXP * kIrfTaps;
+    static constexpr float kTrapz = 0.009f;  // |dk u| below which the trapezoid rule beats the direct difference in fp32
+    struct Par {
+        float a[NEXP], k[NEXP], off;
+        const float* consts = nullptr;  // [W, m0, dt, irf...]
+        const float* tbl = nullptr;     // [NEXP][2][kIrfTaps] of this trial point
+        float m0 = 0.0f, dt = 1.0f, wmax = 0.0f;
+    };
+    struct Step { float da[NEXP], dk[NEXP], doff; };
+    template <class T> struct Geo { T u, w, in; };
+    template <class T> struct Diff { T u; };
+    DPH_HD static void set_consts(Par& q, const float* c) {
+        q.consts = c;
+        if (!c) return;
+        const float w = fminf(fmaxf(c[0], 1.0f), float(kIrfTaps));
+        q.wmax = w - 1.0f; q.m0 = c[1]; q.dt = c[2];
+    }
+    DPH_HD static void prepare(const float* p, Par& q) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) { q.a[i] = p[2 * i]; q.k[i] = p[2 * i + 1]; }
+        q.off = OFFSET ? p[2 * NEXP] : 0.0f;
+    }
+    // prefix sums S, T over the IRF taps for every exponential of the point q, by the lanes of the group
+    template <class L> DPH_HD static void fill_tables(const L& ln, Par& q, float* tbl) {
+        q.tbl = tbl;
+        if (!q.consts) return;  // idle group
+        constexpr int G = L::kLanes;
+        ln.sync();  // the previous pass has finished reading the table
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) {
+            float carry_s = 0.0f, carry_t = 0.0f;
+            const float kd = q.k[i] * q.dt * kLog2e;
+            for (int base = 0; base < kIrfTaps; base += G) {
+                const int w = base + ln.lane;
+                const float tap = float(w) <= q.wmax ? q.consts[3 + w] : 0.0f;
+                float s = tap * f_ex2(kd * float(w));
+                float t = s * (float(w) * q.dt);
+#pragma unroll
+                for (int o = 1; o < G; o <<= 1) {
+                    const float us = ln.up(s, o), ut = ln.up(t, o);
+                    if (ln.lane >= o) { s += us; t += ut; }
+                }
+                s += carry_s; t += carry_t;
+                tbl[(2 * i) * kIrfTaps + w] = s;
+                tbl[(2 * i + 1) * kIrfTaps + w] = t;
+                carry_s = ln.bcast(s, G - 1);
+                carry_t = ln.bcast(t, G - 1);
+            }
+        }
+        ln.sync();
+    }
+    // cy carries the bin index of 1-D data
+    template <class T> DPH_HD static void geometry(const Par& q, T, T cy, Geo<T>& g) {
+        const T jj = cy - T(q.m0);
+        g.u = jj * T(q.dt);
+        g.in = v_nonneg01(jj);
+        g.w = v_clamp(jj, 0.0f, q.wmax);
+    }
+    template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) {
+            const T ex = v_ex2(g.u * T(-kLog2e * q.k[i])) * g.in;
+            const T c = ex * v_gather(q.tbl + (2 * i) * kIrfTaps, g.w);
+            e[2 * i] = c;
+            e[2 * i + 1] = g.u * c - ex * v_gather(q.tbl + (2 * i + 1) * kIrfTaps, g.w);
+        }
+    }
+    template <class T> DPH_HD static T value(const Par& q, const T* e) {
+        T f = T(q.off);
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) f = f_fma(T(q.a[i]), e[2 * i], f);
+        return f;
+    }
+    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>&, const T* e, T* J) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[2 * i]; J[2 * i + 1] = e[2 * i + 1] * T(-q.a[i]); }
+        if (OFFSET) J[2 * NEXP] = T(1.0f);
+    }
+    DPH_HD static void prepare_step(const Par&, const Par&, const float* d, Step& s) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) { s.da[i] = d[2 * i]; s.dk[i] = d[2 * i + 1]; }
+        s.doff = OFFSET ? d[2 * NEXP] : 0.0f;
+    }
+    template <class T> DPH_HD static void diff(const Par&, const Step&, const Geo<T>& g1, Diff<T>& df) { df.u = g1.u; }
+    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
+        T r = T(s.doff);
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) {
+            const T trap = (ea[2 * i + 1] + eb[2 * i + 1]) * T(-0.5f * s.dk[i]);
+            const T dc = v_sel_small(df.u * T(s.dk[i]), kTrapz, trap, eb[2 * i] - ea[2 * i]);
+            r = f_fma(T(s.da[i]), eb[2 * i], f_fma(T(a.a[i]), dc, r));
+        }
+        return r;
+    }
+    template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>&, const T* ea) {
+        T r = T(s.doff);
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) r = f_fma(ea[2 * i], T(s.da[i]), f_fma(ea[2 * i + 1], T(-a.a[i] * s.dk[i]), r));
+        return r;
+    }
+};
+
 // ------------------------------------------------------------------------------ lane group / storage
 // Per-fit pixel state, pointer based so that the device (shared memory) and host builds share code.
 //   y[M]               data (MLE: already clamped to >= 0)
@@ -512,12 +643,14 @@ struct PixelState {
     const float* cy;
     int M, stride;
     int cur;
+    float* tbl = nullptr;  // Mo::kTable floats: per-trial tables of models that need them (fill_tables), else unused
     DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * stride; }
 };
 
 // Group of G lanes.  On the host G == 1 and the reductions are the identity.
 template <int G>
 struct Lanes {
+    static constexpr int kLanes = G;
     int lane;        // index inside the group
     unsigned gmask;  // the warp lanes of this group
 #if defined(__CUDA_ARCH__)
@@ -532,7 +665,13 @@ struct Lanes {
         return v;
     }
     DPH_HD static bool warp_any(bool v) { return __any_sync(0xffffffffu, v); }
+    DPH_HD float up(float v, int o) const { return __shfl_up_sync(gmask, v, o, G); }   // value of lane - o (own value below o)
+    DPH_HD float bcast(float v, int src) const { return __shfl_sync(gmask, v, src, G); }  // value of group lane src
+    DPH_HD void sync() const { __syncwarp(gmask); }
 #else
+    DPH_HD float up(float v, int) const { return v; }
+    DPH_HD float bcast(float v, int) const { return v; }
+    DPH_HD void sync() const {}
     DPH_HD float sum(float v) const { return v; }
     DPH_HD int any(int v) const { return v; }
     DPH_HD static bool warp_any(bool v) { return v; }
@@ -1200,6 +1339,7 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         q1 = st.q0;  // carries the constants of the call (fixed-width model)
         Mo::prepare(xn, q1);
         Mo::prepare_step(st.q0, q1, p, step);
+        Mo::fill_tables(ln, q1, px.tbl);  // models with per-trial tables (IRF-convolved exponentials); no-op otherwise
         const bool init = st.init, want_chi = Lanes<G>::warp_any(pass && st.wants_chi());
         trial_pass<Mo, Stage::kMle, Stage::kPred, true, G>(ln, px, st.q0, q1, step, init, want_chi, nrm);
         if (Stage::kMle && Lanes<G>::warp_any(pass && (nrm.flags & kFlagIrregular))) {

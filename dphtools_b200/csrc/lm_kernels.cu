@@ -42,8 +42,16 @@ int get_ctx(int dev, DeviceCtx** out) {
     return 0;
 }
 
-// number of floats `consts` holds for a model
-int model_consts(int model) { return model == DPHLM_GAUSS2D_INTEGRATED_FIXED ? 1 : 0; }
+// number of floats `consts` holds for a model (host path: `consts` is a host pointer)
+constexpr int kMaxConsts = 3 + 32;
+int model_consts(int model, const float* consts) {
+    if (model == DPHLM_GAUSS2D_INTEGRATED_FIXED) return 1;
+    if (model == DPHLM_MULTI_EXP_IRF && consts) {
+        const int w = (int)consts[0];
+        return 3 + (w < 1 ? 1 : w > 32 ? 32 : w);
+    }
+    return 0;
+}
 
 int auto_group(int M) {
     // measured on B200 (profiles/): 7x7 -> 2 lanes, 11x11 -> 4, 15x15 -> 8, 256 bins -> 16
@@ -70,6 +78,12 @@ int validate_shape(const dphlm_desc* d) {
         case DPHLM_GAUSS2D_INTEGRATED_FIXED:
             if (d->n_param != 4) return fail("gauss2d_integrated_fixed takes 4 parameters");
             if (!d->consts && d->n_fits > 0) return fail("gauss2d_integrated_fixed needs consts[0] = sigma");
+            break;
+        case DPHLM_MULTI_EXP_IRF:
+            if (d->n_param < 2 || d->n_param > 5) return fail("multi_exp_irf supports 2..5 parameters (1-2 exponentials, optional offset)");
+            if (!d->xaxis && d->n_fits > 0) return fail("multi_exp_irf needs xaxis");
+            if (!d->consts && d->n_fits > 0) return fail("multi_exp_irf needs consts = [W, m0, dt, irf[0..W-1]]");
+            if (d->dim1 != 1) return fail("multi_exp_irf is 1-D: dim1 must be 1");
             break;
         case DPHLM_MULTI_EXP:
             if (d->n_param < 2 || d->n_param > 7) return fail("multi_exp supports 2..7 parameters (1-3 exponentials, optional offset)");
@@ -129,6 +143,7 @@ int launch_model(const dphlm_desc* d, int G, const KArgs& a, const ParkLists& pl
         case DPHLM_GAUSS2D_ELLIPTICAL: return launch_gauss2d_elliptical(G, mle, a, pl, ctx, s);
         case DPHLM_GAUSS2D_INTEGRATED: return launch_gauss2d_integrated(G, mle, a, pl, ctx, s);
         case DPHLM_GAUSS2D_INTEGRATED_FIXED: return launch_gauss2d_integrated_fixed(G, mle, a, pl, ctx, s);
+        case DPHLM_MULTI_EXP_IRF: return launch_multi_exp_irf(d->n_param, G, mle, a, pl, ctx, s);
         case DPHLM_MULTI_EXP:
             switch (d->n_param / 2) {
                 case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, pl, ctx, s);
@@ -299,7 +314,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         CUDA_TRY(cudaMemcpyAsync(dp0, d->p0 + lo * P, n * P * 4, cudaMemcpyHostToDevice, s.stream));
         if (d->xaxis) CUDA_TRY(cudaMemcpyAsync(dx, d->xaxis, M * 4, cudaMemcpyHostToDevice, s.stream));
         float* dconsts = reinterpret_cast<float*>(reinterpret_cast<char*>(dx) + align_up(M * 4));
-        const int n_consts = model_consts(d->model);
+        const int n_consts = model_consts(d->model, d->consts);
         if (n_consts) CUDA_TRY(cudaMemcpyAsync(dconsts, d->consts, n_consts * 4, cudaMemcpyHostToDevice, s.stream));
         c.data = ddata; c.p0 = dp0; c.xaxis = d->xaxis ? dx : nullptr; c.consts = n_consts ? dconsts : nullptr;
         c.popt = dpopt; c.info = dinfo; c.nfev = dnfev; c.chisq = dchi;
@@ -341,6 +356,7 @@ int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int ki
         case DPHLM_GAUSS2D_ELLIPTICAL: return launch_cov_gauss2d_elliptical(a, s);
         case DPHLM_GAUSS2D_INTEGRATED: return launch_cov_gauss2d_integrated(a, s);
         case DPHLM_GAUSS2D_INTEGRATED_FIXED: return launch_cov_gauss2d_integrated_fixed(a, s);
+        case DPHLM_MULTI_EXP_IRF: return launch_cov_multi_exp_irf(d->n_param, a, s);
         case DPHLM_MULTI_EXP: return launch_cov_multi_exp(d->n_param, a, s);
     }
     return fail("unknown model id");

@@ -365,7 +365,7 @@ struct IoDevice {
 
 // shared-memory floats of one lane group: two data buffers (working + staged, each with the extra
 // words) and the double-buffered exponentials
-__host__ __device__ inline int group_region(int stride, int ne) { return 2 * (stride + kStageExtra) + 2 * ne * stride; }
+__host__ __device__ inline int group_region(int stride, int ne, int table = 0) { return 2 * (stride + kStageExtra) + 2 * ne * stride + table; }
 
 // CTAs per SM the register allocation is bounded for: 3 (<= 168 registers) where that costs no spills (the symmetric
 // Gaussian, single exponentials); models with more parameters or more per-pixel state declare kMinCtas = 2 (<= 255
@@ -385,15 +385,16 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
     for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
         const int k = i < M ? i : M - 1;
         cx[i] = a.xaxis ? a.xaxis[k] : float(k % a.w);
-        cy[i] = a.xaxis ? 0.0f : float(k / a.w);
+        cy[i] = a.xaxis ? float(k) : float(k / a.w);  // 1-D data: the bin index
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G;
-    const int region = group_region(stride, Mo::NE);
+    const int region = group_region(stride, Mo::NE, Mo::kTable);
     float* base = smem + 2 * ((M + 1) & ~1) + (warp * FPW + grp) * region;
     Lanes<G> ln{lane % G, G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G))};
     PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cx, cy, M, stride, 0};
+    px.tbl = base + region - Mo::kTable;
     IO io{a, base + stride + kStageExtra};
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
     if (a.exit_counter) {  // tell the pollers fed by this kernel when its last CTA has gone
@@ -438,13 +439,15 @@ __global__ void __launch_bounds__(128) dphlm_cov_kernel(const CovArgs a) {
     typename Mo::Par q;
     Mo::set_consts(q, a.consts);
     Mo::prepare(p, q);
+    __shared__ float tables[(128 / G) * (Mo::kTable > 0 ? Mo::kTable : 1)];
+    Mo::fill_tables(ln, q, tables + (threadIdx.x / G) * Mo::kTable);
     Acc<P, float> acc;
     acc.clear();
     const int M = a.h * a.w;
     for (int i = ln.lane; i < M; i += G) {
         typename Mo::template Geo<float> g;
         float e[Mo::NE], J[P];
-        const float cx = a.xaxis ? a.xaxis[i] : float(i % a.w), cy = a.xaxis ? 0.0f : float(i / a.w);
+        const float cx = a.xaxis ? a.xaxis[i] : float(i % a.w), cy = a.xaxis ? float(i) : float(i / a.w);
         Mo::geometry(q, cx, cy, g);
         Mo::expo(q, g, e);
         Mo::jac(q, g, e, J);
@@ -586,8 +589,8 @@ template <class Mo, bool MLE, int G>
 int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t stream) {
     const int M = a0.h * a0.w;
     constexpr int FPW = 32 / G;
-    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE));
-    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE));
+    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE, Mo::kTable));
+    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE, Mo::kTable));
     const bool handoff = G < 32 && pl.cap > 0;
     const int kPollerCtas = budget_from_env("DPHLM_POLLER_CTAS", kPollerCtasDefault);  // tuning aid
     using SA = StageA<Mo>;
@@ -658,6 +661,14 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     return 0;
 }
 
+// models that are only built for wide groups (256-bin histograms)
+#define DPH_DISPATCH_G_WIDE(MO, G, mle, a, pl, ctx, s)                                                    \
+    switch (G) {                                                                                          \
+        case 16: return (mle) ? launch<MO, true, 16>(a, pl, ctx, s) : launch<MO, false, 16>(a, pl, ctx, s); \
+        case 32: return (mle) ? launch<MO, true, 32>(a, pl, ctx, s) : launch<MO, false, 32>(a, pl, ctx, s); \
+    }                                                                                                     \
+    return ::dphlm::fail("this model is built for group_lanes 0, 16 or 32")
+
 // one per model family, defined in lm_inst_*.cu
 int launch_gauss2d(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_gauss2d_elliptical(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
@@ -670,6 +681,8 @@ int launch_cov_gauss2d(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_elliptical(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_integrated(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_integrated_fixed(const CovArgs& a, cudaStream_t s);
+int launch_multi_exp_irf(int n_param, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_cov_multi_exp_irf(int n_param, const CovArgs& a, cudaStream_t s);
 int launch_cov_multi_exp(int n_param, const CovArgs& a, cudaStream_t s);
 
 #define DPH_DISPATCH_G(MO, G, mle, a, pl, ctx, s)                                                     \

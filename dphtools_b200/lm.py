@@ -122,7 +122,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     rejected steps, 0) are ``None`` unless requested.  The call never raises for an individual fit.
     """
     model = _resolve_model(model)
-    one_d = model.model_id == models.MODEL_MULTI_EXP
+    one_d = model.model_id in models.ONE_D
     if _is_torch(data) and data.is_cuda:
         res = _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
                           return_counts, group_lanes, timing, return_x_acc)
@@ -293,7 +293,7 @@ def covariance(model, popt, shape, kind="jtj", xdata=None):
     dim0, dim1 = (shape[0], 1) if len(shape) == 1 else shape
     d = _fill_desc(model, "mle", n_param, dim0, dim1, n, FTOL, XTOL, 0.0, None, 100.0, 0)
     xa = None
-    if model.model_id == models.MODEL_MULTI_EXP:
+    if model.model_id in models.ONE_D:
         if xdata is None:
             raise ValueError("multi_exp needs xdata")
         xa = torch.as_tensor(np.asarray(xdata, dtype=np.float32), device=pt.device).contiguous()
@@ -392,7 +392,7 @@ def curve_fit(f, xdata, ydata, p0=None, sigma=None, absolute_sigma=False, check_
     p0 = np.atleast_1d(np.asarray(p0, dtype=float))
     if p0.size > ydata.size:
         raise TypeError("Improper input: func input vector length N=%d must not exceed func output vector length M=%d" % (p0.size, ydata.size))
-    if model.model_id == models.MODEL_MULTI_EXP:
+    if model.model_id in models.ONE_D:
         data, xa = ydata.reshape(1, -1), xdata.ravel()
     else:
         shape = _grid_shape(xdata)

@@ -17,6 +17,8 @@ Conventions:
   (erf model of a pixelated camera); ``amp`` is the photon count of the spot.
 * ``gauss2d_integrated_fixed(sigma)``: factory for the 4-parameter ``(amp, x0, y0, offset)`` version with the width held
   at ``sigma`` (the model of ``notebooks/MLE_LevMarq_4Param_2013_11_12.m`` upstream, whose PSF width is a call argument).
+* ``multi_exp_convolved(irf, dt, m0)``: factory for ``multi_exp`` convolved with an instrument response function sampled on
+  the histogram's own grid (lifetime histograms): ``f_j = offset + sum_i a_i sum_q irf[q] exp(-k_i (j - m0 - q) dt)``.
 * ``gauss2d_elliptical``: ``u =  c (x-x0) + s (y-y0)``, ``v = -s (x-x0) + c (y-y0)``,
   ``amp * exp(-(u^2/sigma_x^2 + v^2/sigma_y^2)/2) + offset`` with ``c, s = cos, sin(theta)``.
 """
@@ -29,6 +31,9 @@ MODEL_GAUSS2D_ELLIPTICAL = 1
 MODEL_MULTI_EXP = 2
 MODEL_GAUSS2D_INTEGRATED = 3
 MODEL_GAUSS2D_INTEGRATED_FIXED = 4
+MODEL_MULTI_EXP_IRF = 5
+ONE_D = (MODEL_MULTI_EXP, MODEL_MULTI_EXP_IRF)  # models of a 1-D histogram: need the shared x axis
+IRF_MAX_TAPS = 32
 
 
 def gauss2d(xy, amp, x0, y0, sigma, offset):
@@ -152,6 +157,53 @@ def multi_exp_jac(xdata, *args):
     return np.stack(cols, axis=1)
 
 
+def multi_exp_convolved(irf, dt, m0=0):
+    """Sum of exponentials convolved with an instrument response function: returns the model ``f(x, a0, k0, ..., [offset])``
+    (parameters as :func:`multi_exp`) with ``f.jac``.  ``irf`` holds the ``W <= 32`` response taps on the histogram's own
+    uniform grid of spacing ``dt``, the first one at bin ``m0``:
+
+        ``f_j = offset + sum_i a_i C_i[j]``,  ``C_i[j] = sum_{q=0}^{min(j-m0, W-1)} irf[q] exp(-k_i (j - m0 - q) dt)``
+
+    (bins before ``m0`` see only the offset).  ``x`` must be that grid (any origin); only its length is used.
+    ``f.consts = (W, m0, dt, *irf)`` travels to the kernels as ``dphlm_desc.consts``.  (the model
+    is our own discrete formulation.)"""
+    irf = np.asarray(irf, dtype=np.float32).astype(float).ravel()  # the kernels see float32 taps
+    dt, m0 = float(np.float32(dt)), int(m0)
+    if not 1 <= irf.size <= IRF_MAX_TAPS:
+        raise ValueError("irf must have 1..%d taps" % IRF_MAX_TAPS)
+    if not dt > 0 or m0 < 0:
+        raise ValueError("dt must be positive and m0 non-negative")
+
+    def _lags(xdata):
+        j = np.arange(np.asarray(xdata).size)
+        lag = (j[:, None] - m0 - np.arange(irf.size)[None, :]) * dt  # (M, W)
+        return lag, lag >= 0
+
+    def _cd(xdata, k):
+        lag, ok = _lags(xdata)
+        term = np.where(ok, irf[None, :] * np.exp(-k * np.where(ok, lag, 0.0)), 0.0)
+        return term.sum(1), (term * lag).sum(1)
+
+    def model(xdata, *args):
+        res = np.full(np.asarray(xdata).size, args[-1] if len(args) % 2 else 0.0, dtype=float)
+        for i in range(len(args) // 2):
+            res = res + args[2 * i] * _cd(xdata, args[2 * i + 1])[0]
+        return res
+
+    def jac(xdata, *args):
+        cols = []
+        for i in range(len(args) // 2):
+            c, d = _cd(xdata, args[2 * i + 1])
+            cols += [c, -args[2 * i] * d]
+        if len(args) % 2:
+            cols.append(np.ones(np.asarray(xdata).size))
+        return np.stack(cols, axis=1)
+
+    _tag(model, jac, MODEL_MULTI_EXP_IRF, None, "multi_exp_convolved")
+    model.consts = (float(irf.size), float(m0), dt) + tuple(float(v) for v in irf)
+    return model
+
+
 def _tag(func, jac, model_id, n_param, name):
     func.jac = jac
     func.model_id = model_id
@@ -169,9 +221,12 @@ BUILTIN = {m.model_name: m for m in (gauss2d, gauss2d_elliptical, multi_exp, gau
 
 
 def resolve(name, consts=None):
-    """Model by name; ``gauss2d_integrated_fixed`` is built from ``consts = (sigma,)``."""
+    """Model by name; the factories are called with the constants they stored in ``f.consts``."""
     if name == "gauss2d_integrated_fixed":
         return gauss2d_integrated_fixed(consts[0])
+    if name == "multi_exp_convolved":
+        w = int(consts[0])
+        return multi_exp_convolved(consts[3:3 + w], consts[2], int(consts[1]))
     return BUILTIN[name]
 
 

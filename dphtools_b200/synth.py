@@ -154,6 +154,46 @@ def multi_exp_hists(n, bins=256, seed=0):
     return dict(data=data, p0=multi_exp_p0(data), truth=truth, xaxis=x)
 
 
+def default_irf(taps=16, sigma_bins=1.7):
+    """Gaussian instrument response, ``taps`` bins wide, unit sum, float32."""
+    q = np.arange(taps)
+    g = np.exp(-0.5 * ((q - (taps - 1) / 2) / sigma_bins) ** 2)
+    return (g / g.sum()).astype(np.float32)
+
+
+def multi_exp_irf_hists(n, bins=256, seed=0, dt=0.05, m0=8):
+    """Bi-exponential lifetime histograms seen through an instrument response (:func:`default_irf` starting at bin ``m0``);
+    the bins before ``m0`` hold only the offset.  Guess: offset from those bins, 65/35 split of the peak height, fixed rates."""
+    rng = np.random.default_rng(seed)
+    irf = default_irf()
+    model = models.multi_exp_convolved(irf, dt, m0)
+    x = (dt * np.arange(bins)).astype(np.float32)
+    truth = np.stack(
+        [rng.uniform(200, 2000, n), rng.uniform(1.5, 3.0, n), rng.uniform(100, 1000, n), rng.uniform(0.2, 0.6, n), rng.uniform(1, 10, n)],
+        axis=1,
+    )
+    lag = (np.arange(bins)[:, None] - m0 - np.arange(irf.size)[None, :]) * float(np.float32(dt))
+    ok = lag >= 0
+    lag0 = np.where(ok, lag, 0.0)
+    w = np.where(ok, irf.astype(float)[None, :], 0.0)
+    data = np.empty((n, bins), dtype=np.float32)
+    step = 8192
+    for lo in range(0, n, step):
+        t = truth[lo : lo + step]
+        c0 = (w[None] * np.exp(-t[:, 1, None, None] * lag0[None])).sum(2)
+        c1 = (w[None] * np.exp(-t[:, 3, None, None] * lag0[None])).sum(2)
+        data[lo : lo + step] = rng.poisson(t[:, 0:1] * c0 + t[:, 2:3] * c1 + t[:, 4:5])
+    off = data[:, : max(m0 - 2, 1)].mean(1)
+    amp = np.maximum(data.max(1) - off, 1.0)
+    p0 = np.empty((n, 5), dtype=np.float32)
+    p0[:, 0] = 0.65 * amp
+    p0[:, 1] = 2.2
+    p0[:, 2] = 0.35 * amp
+    p0[:, 3] = 0.4
+    p0[:, 4] = np.maximum(off, 0.5)
+    return dict(data=data, p0=p0, truth=truth, xaxis=x, consts=model.consts)
+
+
 WORKLOADS = {
     "c1_gauss2d_15": lambda n, seed=0: gauss2d_rois(n, 15, seed, photons=(1500.0, 1500.0), sigma=(1.38, 1.38)),
     "c2_gauss2d_11": lambda n, seed=0: gauss2d_rois(n, 11, seed),
@@ -162,4 +202,5 @@ WORKLOADS = {
     "c5_multiexp_256": lambda n, seed=0: multi_exp_hists(n, 256, seed),
     "c6_gauss2d_int_11": lambda n, seed=0: gauss2d_integrated_rois(n, 11, seed),
     "c7_gauss2d_intf_11": lambda n, seed=0: gauss2d_integrated_fixed_rois(n, 11, seed),
+    "c8_multiexp_irf_256": lambda n, seed=0: multi_exp_irf_hists(n, 256, seed),
 }

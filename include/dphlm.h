@@ -25,10 +25,13 @@ extern "C" {
  * GAUSS2D (amp, x0, y0, sigma, offset), GAUSS2D_ELLIPTICAL (amp, x0, y0, sigma_x, sigma_y, theta, offset) sampled at
  * the pixel centres; GAUSS2D_INTEGRATED (photons, x0, y0, sigma, offset) integrated over each pixel (erf model);
  * GAUSS2D_INTEGRATED_FIXED (photons, x0, y0, offset) the same with the width held at consts[0] (the 4-parameter model of
- * notebooks/MLE_LevMarq_4Param_2013_11_12.m:44-54, where the PSF width is an argument of the call). */
+ * notebooks/MLE_LevMarq_4Param_2013_11_12.m:44-54, where the PSF width is an argument of the call);
+ * MULTI_EXP_IRF: MULTI_EXP (1-2 exponentials, optional offset) convolved with an instrument response function given on the
+ * histogram's own uniform grid: f_j = offset + sum_i a_i sum_q irf[q] exp(-k_i (j - m0 - q) dt) over 0 <= q < W, q <= j - m0;
+ * consts = [W (<= 32), m0, dt, irf[0..W-1]].  Built for group_lanes 0, 16, 32. */
 enum dphlm_model {
     DPHLM_GAUSS2D = 0, DPHLM_GAUSS2D_ELLIPTICAL = 1, DPHLM_MULTI_EXP = 2, DPHLM_GAUSS2D_INTEGRATED = 3,
-    DPHLM_GAUSS2D_INTEGRATED_FIXED = 4
+    DPHLM_GAUSS2D_INTEGRATED_FIXED = 4, DPHLM_MULTI_EXP_IRF = 5
 };
 
 /* `method` of curve_fit / lm (dphtools/utils/lm.py:235, 519, 621-626) */
@@ -50,7 +53,7 @@ typedef struct dphlm_desc {
     int32_t group_lanes; /* lanes of a warp that own one fit: 0 = automatic, else 2, 4, 8, 16 or 32 */
     int64_t n_fits;
     const float* data;   /* [n_fits, dim0, dim1] ydata, row-major (uint16 with DPHLM_FLAG_DATA_U16)  (lm.py:512) */
-    const float* xaxis;  /* MULTI_EXP: [dim0] shared xdata; NULL for 2-D models (pixel indices)        */
+    const float* xaxis;  /* MULTI_EXP(_IRF): [dim0] shared xdata; NULL for 2-D models (pixel indices)   */
     const float* p0;     /* [n_fits, n_param] initial guesses                               (lm.py:514) */
     float* popt;         /* [n_fits, n_param] fitted parameters                             (lm.py:682) */
     int32_t* info;       /* [n_fits]                                                        (lm.py:669) */
@@ -63,7 +66,8 @@ typedef struct dphlm_desc {
     float ftol, xtol, gtol, factor; /* lm()/leastsq keywords, forwarded to both stages (lm.py:643, 668) */
     int32_t maxfev;      /* <= 0: 100 * (n_param + 1)                                   (lm.py:306-307) */
     int32_t flags;       /* DPHLM_FLAG_* */
-    const float* consts; /* constants of the model, shared by all fits: GAUSS2D_INTEGRATED_FIXED: [1] sigma; else NULL */
+    const float* consts; /* constants of the model, shared by all fits: GAUSS2D_INTEGRATED_FIXED: [1] sigma;
+                            MULTI_EXP_IRF: [3 + W] = W, m0, dt, irf[0..W-1]; else NULL */
 } dphlm_desc;
 
 /* flags: record CUDA events around the two kernels of dphlm_fit_batch (read with dphlm_last_kernel_ms) */

@@ -125,7 +125,7 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
     float* cx = reinterpret_cast<float*>(backing.data());
     float* cy = cx + stride;
     for (int i = 0; i < M; ++i) {
-        if (xaxis) { cx[i] = xaxis[i]; cy[i] = 0.f; }
+        if (xaxis) { cx[i] = xaxis[i]; cy[i] = float(i); }  // 1-D data: cy = bin index
         else { cx[i] = float(i % w); cy[i] = float(i / w); }
     }
     std::vector<double> ybuf(stride), ebuf(Mo::NE * stride);
@@ -133,6 +133,8 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
     float* e = reinterpret_cast<float*>(ebuf.data());
     Lanes<1> ln{0, 1u};
     PixelState<Mo::NE> px{y, e, cx, cy, M, stride, 0};
+    std::vector<float> table(Mo::kTable + 1);
+    px.tbl = table.data();
     HostIoPrefit<Mo> ioa{b};
     run_stage<StageA<Mo>, Mo, 1>(ln, px, opt, ioa);
     b.parked.clear();
@@ -157,6 +159,10 @@ extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, l
     if (model == 1 && n_param == 7) RUN(Gauss2DElliptical);
     if (model == 3 && n_param == 5) RUN(Gauss2DIntegrated);
     if (model == 4 && n_param == 4 && consts) RUN(Gauss2DIntegratedFixed);
+    if (model == 5 && n_param == 2 && consts) RUN(MultiExpIrf<1, false>);
+    if (model == 5 && n_param == 3 && consts) RUN(MultiExpIrf<1, true>);
+    if (model == 5 && n_param == 4 && consts) RUN(MultiExpIrf<2, false>);
+    if (model == 5 && n_param == 5 && consts) RUN(MultiExpIrf<2, true>);
     if (model == 2 && n_param == 2) RUN(MultiExp<1, false>);
     if (model == 2 && n_param == 3) RUN(MultiExp<1, true>);
     if (model == 2 && n_param == 4) RUN(MultiExp<2, false>);

@@ -41,9 +41,10 @@ SETS = {
     "c5_ls": ("c5_multiexp_256", 2000, 15, "ls"),
     "c6_mle": ("c6_gauss2d_int_11", 2000, 6, "mle"),
     "c7_mle": ("c7_gauss2d_intf_11", 2000, 7, "mle"),
+    "c8_mle": ("c8_multiexp_irf_256", 1000, 8, "mle"),
 }
 MODEL_OF = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp, "c6": models.gauss2d_integrated,
-            "c7": models.gauss2d_integrated_fixed(1.3)}
+            "c7": models.gauss2d_integrated_fixed(1.3), "c8": models.multi_exp_convolved([1.0], 1.0)}
 
 _G = {}
 

@@ -26,7 +26,7 @@ ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 w = synth.WORKLOADS[a.workload](a.n, seed=1)
 data, p0 = torch.from_numpy(w["data"]).cuda(), torch.from_numpy(w["p0"]).cuda()
-model = MODEL[a.workload[:2]]
+model = models.resolve("multi_exp_convolved", w["consts"]) if a.workload.startswith("c8") else MODEL[a.workload[:2]]
 for lanes in a.lanes:
     ts = []
     for r in range(a.reps):

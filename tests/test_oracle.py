@@ -6,7 +6,7 @@ import pytest
 from dphtools_b200 import models
 from oracle import lm_oracle
 
-SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle", "c7_mle"]
+SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle", "c7_mle", "c8_mle"]
 
 
 def _xdata(g):
@@ -53,10 +53,12 @@ def test_oracle_curve_fit_surface(golden):
     (models.gauss2d_integrated, (1500.0, 7.3, 6.6, 1.4, 3.0)),
     (models.gauss2d_integrated_fixed(1.25), (1500.0, 7.3, 6.6, 3.0)),
     (models.multi_exp, (900.0, 2.2, 300.0, 0.4, 4.0)),
+    (models.multi_exp_convolved([0.1, 0.2, 0.4, 0.2, 0.1], 0.05, 6), (900.0, 2.2, 300.0, 0.4, 4.0)),
+    (models.multi_exp_convolved([0.1, 0.2, 0.4, 0.2, 0.1], 0.05, 6), (900.0, 2.2)),
     (models.multi_exp, (900.0, 2.2, 300.0, 0.4)),
 ])
 def test_jacobians_against_central_differences(model, p):
-    x = 0.05 * np.arange(256) if model is models.multi_exp else models.roi_grid(15, 15)
+    x = 0.05 * np.arange(256) if model.model_id in models.ONE_D else models.roi_grid(15, 15)
     p = np.array(p)
     jac = model.jac(x, *p)
     for k in range(p.size):
