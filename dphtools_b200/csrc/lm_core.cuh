@@ -111,6 +111,20 @@ DPH_HD float v_pick(bool c, float x, float y) { return c ? x : y; }
 DPH_HD f2 v_pick(bool c, f2 x, f2 y) { return f2(c ? x.x : y.x, c ? x.y : y.y); }
 DPH_HD float v_gather(const float* t, float i) { return t[int(i)]; }  // table lookup by (integer-valued) index
 DPH_HD f2 v_gather(const float* t, f2 i) { return f2(t[int(i.x)], t[int(i.y)]); }
+struct alignas(16) quad { float x, y, z, w; };
+struct alignas(8) duo { float x, y; };
+template <class T> struct Q4 { T a, b, c, d; };
+template <class T> struct Q2 { T a, b; };
+DPH_HD Q4<float> v_gather4(const float* t, float i) { const quad v = reinterpret_cast<const quad*>(t)[int(i)]; return {v.x, v.y, v.z, v.w}; }
+DPH_HD Q4<f2> v_gather4(const float* t, f2 i) {
+    const quad u = reinterpret_cast<const quad*>(t)[int(i.x)], v = reinterpret_cast<const quad*>(t)[int(i.y)];
+    return {f2(u.x, v.x), f2(u.y, v.y), f2(u.z, v.z), f2(u.w, v.w)};
+}
+DPH_HD Q2<float> v_gather2(const float* t, float i) { const duo v = reinterpret_cast<const duo*>(t)[int(i)]; return {v.x, v.y}; }
+DPH_HD Q2<f2> v_gather2(const float* t, f2 i) {
+    const duo u = reinterpret_cast<const duo*>(t)[int(i.x)], v = reinterpret_cast<const duo*>(t)[int(i.y)];
+    return {f2(u.x, v.x), f2(u.y, v.y)};
+}
 DPH_HD float v_clamp(float a, float lo, float hi) { return fminf(fmaxf(a, lo), hi); }
 DPH_HD f2 v_clamp(f2 a, float lo, float hi) { return f2(fminf(fmaxf(a.x, lo), hi), fminf(fmaxf(a.y, lo), hi)); }
 DPH_HD float v_nonneg01(float a) { return a >= 0.0f ? 1.0f : 0.0f; }  // 1 where a >= 0, else 0
@@ -234,7 +248,8 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     template <class T> struct Geo { T dx, dy, r2; };
     template <class T> struct Diff { T dot, dr2, r20; };
     static constexpr int kTable = 0;
-    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
+    DPH_HD static int table_floats(int, int) { return 0; }
+    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
@@ -285,7 +300,8 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     template <class T> struct Geo { T dx, dy, u, v; };
     template <class T> struct Diff { T dx, dy, u, v; };
     static constexpr int kTable = 0;
-    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
+    DPH_HD static int table_floats(int, int) { return 0; }
+    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];
@@ -368,16 +384,29 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
 // Pixel-integrated symmetric Gaussian (erf model of a pixelated camera; SURVEY.md 8(f) rank 4, cf. upstream
 // notebooks/MLE_LevMarq_4Param_2013_11_12.m:44-46): amp * Ex(x) * Ey(y) + offset with
 // Ex = (erf((x - x0 + 1/2) a) - erf((x - x0 - 1/2) a)) / 2, a = 1 / (sqrt(2) sigma).  amp, x0, y0, sigma, offset.
-// It uses the GENERIC step difference any model with a Jacobian can use: for small steps
-// f(x + d) - f(x) = J(x + d/2) d + O(d^3) (midpoint rule; relative error ~ (d/scale)^2 / 24), for large steps the
-// direct difference; the switch sits where both have the same absolute error (~1e-7 f).
+// The model is SEPARABLE, so every transcendental is evaluated per column and per row of the ROI (w + h axis positions per
+// trial point instead of w h pixels): fill_tables() computes, cooperatively over the lanes of the group and into the group's
+// shared memory, for every axis position
+//   A = (E_b, dE_b/dc, dE_b/dsigma, E_b - E_a)   at the trial point b,     B = (E_a, J_axis(a) . d)   at the accepted point a,
+// and the pixel loop only gathers and multiplies.  The axis difference E_b - E_a uses the step difference any function
+// with a derivative can use: for small steps E(x + d) - E(x) = E'(x + d/2) d + O(d^3) (midpoint rule; relative error
+// ~ (d/scale)^2 / 24), for large steps the direct difference; the switch sits where both have the same absolute error.
+// Then  f_b - f_a = d_amp E_bx E_by + amp_a (dEx E_by + E_ax dEy) + d_off  without cancellation.
 template <bool FIXED>
 struct Gauss2DIntegratedT {
     static constexpr int P = FIXED ? 4 : 5, NE = 1, kMinCtas = 2, kOff = P - 1;
-    struct Par { float amp, x0, y0, sig = 1.0f, off, a = 0.70710678118654752f, c = 0.39894228040143268f, cs = 0.39894228040143268f; };
+    static constexpr int kAxisMax = 32;                // ROI side limit (validated by the entry points)
+    static constexpr int kTable = 6 * 2 * kAxisMax;    // static bound, used by the covariance kernel
+    DPH_HD static int table_floats(int h, int w) { return (6 * (h + w) + 3) & ~3; }
+    struct Par {
+        float amp, x0, y0, sig = 1.0f, off, a = 0.70710678118654752f, c = 0.39894228040143268f, cs = 0.39894228040143268f;
+        const float* tbl = nullptr;  // tables of the trial point this Par describes (fill_tables)
+        float w = 0.0f;              // ROI width: rows follow the columns in the tables
+        int n = 0;                   // w + h
+    };
     struct Step { float d[P]; Par mid; bool direct; };
-    template <class T> struct Geo { T cx, cy, ex, ey, dex, dey, sex, sey; };
-    template <class T> struct Diff { T cx, cy; };
+    template <class T> struct Geo { T ex, ey, dex, dey, sex, sey, dEx, dEy, exa, eya, ux, uy; };
+    template <class T> struct Diff { T dEx, dEy, exa, eya, eyb, ux, uy; };
     DPH_HD static void set_sigma(Par& q, float sig) {
         q.sig = sig;
         const float is = f_rcp(sig);
@@ -386,8 +415,6 @@ struct Gauss2DIntegratedT {
         q.cs = q.c * is;
     }
     // FIXED: the width is a constant of the call (consts[0]); prepare() leaves it alone
-    static constexpr int kTable = 0;
-    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
     DPH_HD static void set_consts(Par& q, const float* consts) {
         if (FIXED && consts) set_sigma(q, consts[0]);
     }
@@ -396,18 +423,41 @@ struct Gauss2DIntegratedT {
         if (!FIXED) set_sigma(q, p[3]);
     }
     // pixel integral of the unit-area Gaussian along one axis and its derivatives w.r.t. centre and sigma
-    template <class T> DPH_HD static void axis(const Par& q, T t, T& e, T& de, T& se) {
-        const T tp = t + T(0.5f), tm = t - T(0.5f);
-        const T zp = tp * T(q.a), zm = tm * T(q.a);
-        e = (v_erf(zp) - v_erf(zm)) * T(0.5f);
-        const T gp = v_ex2(zp * zp * T(-kLog2e)), gm = v_ex2(zm * zm * T(-kLog2e));
-        de = (gm - gp) * T(q.c);
-        se = (tm * gm - tp * gp) * T(q.cs);
+    DPH_HD static void axis(const Par& q, float t, float& e, float& de, float& se) {
+        const float tp = t + 0.5f, tm = t - 0.5f;
+        const float zp = tp * q.a, zm = tm * q.a;
+        e = (erff(zp) - erff(zm)) * 0.5f;
+        const float gp = f_ex2(zp * zp * -kLog2e), gm = f_ex2(zm * zm * -kLog2e);
+        de = (gm - gp) * q.c;
+        se = (tm * gm - tp * gp) * q.cs;
+    }
+    template <class L> DPH_HD static void fill_tables(const L& ln, const Par& q0, Par& q1, Step& st, float* tbl, int h, int w) {
+        const int n = h + w;
+        q1.tbl = tbl; q1.w = float(w); q1.n = n;
+        quad* A = reinterpret_cast<quad*>(tbl);
+        duo* B = reinterpret_cast<duo*>(tbl + 4 * n);
+        ln.sync();  // the previous pass has finished reading the tables
+        for (int t = ln.lane; t < n; t += L::kLanes) {
+            const bool row = t >= w;
+            const float pos = float(row ? t - w : t);
+            const float dc = row ? st.d[2] : st.d[1], ds = FIXED ? 0.0f : st.d[FIXED ? 0 : 3];
+            float ea, dea, sea, eb, deb, seb, em, dem, sem;
+            axis(q0, pos - (row ? q0.y0 : q0.x0), ea, dea, sea);
+            axis(q1, pos - (row ? q1.y0 : q1.x0), eb, deb, seb);
+            axis(st.mid, pos - (row ? st.mid.y0 : st.mid.x0), em, dem, sem);
+            const float dE = st.direct ? eb - ea : f_fma(dem, dc, sem * ds);
+            A[t] = quad{eb, deb, seb, dE};
+            B[t] = duo{ea, f_fma(dea, dc, sea * ds)};
+        }
+        ln.sync();
     }
     template <class T> DPH_HD static void geometry(const Par& q, T cx, T cy, Geo<T>& g) {
-        g.cx = cx; g.cy = cy;
-        axis(q, cx - T(q.x0), g.ex, g.dex, g.sex);
-        axis(q, cy - T(q.y0), g.ey, g.dey, g.sey);
+        const T r = cy + T(q.w);
+        const Q4<T> ca = v_gather4(q.tbl, cx), ra = v_gather4(q.tbl, r);
+        const Q2<T> cb = v_gather2(q.tbl + 4 * q.n, cx), rb = v_gather2(q.tbl + 4 * q.n, r);
+        g.ex = ca.a; g.dex = ca.b; g.sex = ca.c; g.dEx = ca.d;
+        g.ey = ra.a; g.dey = ra.b; g.sey = ra.c; g.dEy = ra.d;
+        g.exa = cb.a; g.ux = cb.b; g.eya = rb.a; g.uy = rb.b;
     }
     template <class T> DPH_HD static void expo(const Par&, const Geo<T>& g, T* e) { e[0] = g.ex * g.ey; }
     template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
@@ -428,28 +478,20 @@ struct Gauss2DIntegratedT {
         s.mid = a;
         prepare(pm, s.mid);
         const float is = f_rcp(fabsf(a.sig));
-        float rel = fmaxf(fabsf(d[0]) * f_rcp(fabsf(a.amp) + 1e-30f), fmaxf(fabsf(d[1]), fabsf(d[2])) * is);
+        float rel = fmaxf(fabsf(d[1]), fabsf(d[2])) * is;
         if (!FIXED) rel = fmaxf(rel, fabsf(d[3]) * is);
         s.direct = !(rel <= 0.015625f);
     }
-    template <class T> DPH_HD static void diff(const Par&, const Step&, const Geo<T>& g1, Diff<T>& df) { df.cx = g1.cx; df.cy = g1.cy; }
-    template <class T> DPH_HD static T jdot(const Par& q, const float* d, T cx, T cy) {  // J(q) . d at one pixel
-        Geo<T> g;
-        T e[1], J[P];
-        geometry(q, cx, cy, g);
-        expo(q, g, e);
-        jac(q, g, e, J);
-        T r = T(d[kOff]);
-#pragma unroll
-        for (int k = 0; k < kOff; ++k) r = f_fma(J[k], T(d[k]), r);
-        return r;
+    template <class T> DPH_HD static void diff(const Par&, const Step&, const Geo<T>& g1, Diff<T>& df) {
+        df.dEx = g1.dEx; df.dEy = g1.dEy; df.exa = g1.exa; df.eya = g1.eya; df.eyb = g1.ey; df.ux = g1.ux; df.uy = g1.uy;
     }
-    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
-        if (s.direct) return f_fma(T(a.amp + s.d[0]), eb[0], T(s.d[kOff])) - T(a.amp) * ea[0];
-        return jdot(s.mid, s.d, df.cx, df.cy);
+    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T*, const T* eb) {
+        const T de = f_fma(df.dEx, df.eyb, df.exa * df.dEy);  // E_bx E_by - E_ax E_ay
+        return f_fma(T(s.d[0]), eb[0], f_fma(T(a.amp), de, T(s.d[kOff])));
     }
-    template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& df, const T*) {
-        return jdot(a, s.d, df.cx, df.cy);
+    template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& df, const T* ea) {
+        const T u = f_fma(df.ux, df.eya, df.exa * df.uy);     // J_(x0, y0, sigma)(a) . d / amp
+        return f_fma(T(s.d[0]), ea[0], f_fma(T(a.amp), u, T(s.d[kOff])));
     }
 };
 using Gauss2DIntegrated = Gauss2DIntegratedT<false>;       // (photons, x0, y0, sigma, offset)
@@ -464,7 +506,8 @@ struct MultiExp {
     template <class T> struct Geo { T x; };
     template <class T> struct Diff { T x; };
     static constexpr int kTable = 0;
-    template <class L> DPH_HD static void fill_tables(const L&, Par&, float*) {}
+    DPH_HD static int table_floats(int, int) { return 0; }
+    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
 #pragma unroll
@@ -527,6 +570,7 @@ template <int NEXP, bool OFFSET>
 struct MultiExpIrf {
     static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = 2 * NEXP, kMinCtas = 2;
     static constexpr int kTable = 2 * NEXP * kIrfTaps;
+    DPH_HD static int table_floats(int, int) { return kTable; }
     static constexpr float kTrapz = 0.009f;  // |dk u| below which the trapezoid rule beats the direct difference in fp32
     struct Par {
         float a[NEXP], k[NEXP], off;
@@ -549,7 +593,7 @@ struct MultiExpIrf {
         q.off = OFFSET ? p[2 * NEXP] : 0.0f;
     }
     // prefix sums S, T over the IRF taps for every exponential of the point q, by the lanes of the group
-    template <class L> DPH_HD static void fill_tables(const L& ln, Par& q, float* tbl) {
+    template <class L> DPH_HD static void fill_tables(const L& ln, const Par&, Par& q, Step&, float* tbl, int, int) {
         q.tbl = tbl;
         if (!q.consts) return;  // idle group
         constexpr int G = L::kLanes;
@@ -643,7 +687,8 @@ struct PixelState {
     const float* cy;
     int M, stride;
     int cur;
-    float* tbl = nullptr;  // Mo::kTable floats: per-trial tables of models that need them (fill_tables), else unused
+    float* tbl = nullptr;  // Mo::table_floats(h, w): per-trial tables of models that need them (fill_tables), else unused
+    int w = 1;             // row length of a 2-D ROI (M / w rows)
     DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * stride; }
 };
 
@@ -1339,7 +1384,7 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         q1 = st.q0;  // carries the constants of the call (fixed-width model)
         Mo::prepare(xn, q1);
         Mo::prepare_step(st.q0, q1, p, step);
-        Mo::fill_tables(ln, q1, px.tbl);  // models with per-trial tables (IRF-convolved exponentials); no-op otherwise
+        Mo::fill_tables(ln, st.q0, q1, step, px.tbl, px.M / px.w, px.w);  // models with per-trial tables; no-op otherwise
         const bool init = st.init, want_chi = Lanes<G>::warp_any(pass && st.wants_chi());
         trial_pass<Mo, Stage::kMle, Stage::kPred, true, G>(ln, px, st.q0, q1, step, init, want_chi, nrm);
         if (Stage::kMle && Lanes<G>::warp_any(pass && (nrm.flags & kFlagIrregular))) {

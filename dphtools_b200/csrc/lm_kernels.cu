@@ -74,9 +74,11 @@ int validate_shape(const dphlm_desc* d) {
             break;
         case DPHLM_GAUSS2D_INTEGRATED:
             if (d->n_param != 5) return fail("gauss2d_integrated takes 5 parameters");
+            if (d->dim0 > 32 || d->dim1 > 32) return fail("gauss2d_integrated: ROI sides up to 32 pixels");
             break;
         case DPHLM_GAUSS2D_INTEGRATED_FIXED:
             if (d->n_param != 4) return fail("gauss2d_integrated_fixed takes 4 parameters");
+            if (d->dim0 > 32 || d->dim1 > 32) return fail("gauss2d_integrated_fixed: ROI sides up to 32 pixels");
             if (!d->consts && d->n_fits > 0) return fail("gauss2d_integrated_fixed needs consts[0] = sigma");
             break;
         case DPHLM_MULTI_EXP_IRF:

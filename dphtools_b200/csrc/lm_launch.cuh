@@ -390,11 +390,13 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G;
-    const int region = group_region(stride, Mo::NE, Mo::kTable);
+    const int table = Mo::table_floats(a.h, a.w);
+    const int region = group_region(stride, Mo::NE, table);
     float* base = smem + 2 * ((M + 1) & ~1) + (warp * FPW + grp) * region;
     Lanes<G> ln{lane % G, G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G))};
     PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cx, cy, M, stride, 0};
-    px.tbl = base + region - Mo::kTable;
+    px.tbl = base + region - table;
+    px.w = a.w;
     IO io{a, base + stride + kStageExtra};
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
     if (a.exit_counter) {  // tell the pollers fed by this kernel when its last CTA has gone
@@ -439,8 +441,16 @@ __global__ void __launch_bounds__(128) dphlm_cov_kernel(const CovArgs a) {
     typename Mo::Par q;
     Mo::set_consts(q, a.consts);
     Mo::prepare(p, q);
-    __shared__ float tables[(128 / G) * (Mo::kTable > 0 ? Mo::kTable : 1)];
-    Mo::fill_tables(ln, q, tables + (threadIdx.x / G) * Mo::kTable);
+    __shared__ __align__(16) float tables[(128 / G) * (Mo::kTable > 0 ? Mo::kTable : 4)];
+    {
+        float zero[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) zero[k] = 0.0f;
+        typename Mo::Step st;
+        Mo::prepare_step(q, q, zero, st);
+        const typename Mo::Par q0 = q;
+        Mo::fill_tables(ln, q0, q, st, tables + (threadIdx.x / G) * Mo::kTable, a.h, a.w);
+    }
     Acc<P, float> acc;
     acc.clear();
     const int M = a.h * a.w;
@@ -589,8 +599,8 @@ template <class Mo, bool MLE, int G>
 int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t stream) {
     const int M = a0.h * a0.w;
     constexpr int FPW = 32 / G;
-    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE, Mo::kTable));
-    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE, Mo::kTable));
+    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE, Mo::table_floats(a0.h, a0.w)));
+    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE, Mo::table_floats(a0.h, a0.w)));
     const bool handoff = G < 32 && pl.cap > 0;
     const int kPollerCtas = budget_from_env("DPHLM_POLLER_CTAS", kPollerCtasDefault);  // tuning aid
     using SA = StageA<Mo>;

@@ -133,8 +133,9 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
     float* e = reinterpret_cast<float*>(ebuf.data());
     Lanes<1> ln{0, 1u};
     PixelState<Mo::NE> px{y, e, cx, cy, M, stride, 0};
-    std::vector<float> table(Mo::kTable + 1);
-    px.tbl = table.data();
+    std::vector<double> table(Mo::table_floats(h, w) / 2 + 2);  // double: 16-byte aligned by operator new
+    px.tbl = reinterpret_cast<float*>(table.data());
+    px.w = w;
     HostIoPrefit<Mo> ioa{b};
     run_stage<StageA<Mo>, Mo, 1>(ln, px, opt, ioa);
     b.parked.clear();
