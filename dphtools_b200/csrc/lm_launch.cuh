@@ -73,6 +73,7 @@ struct KArgs {
     int* error_flag;        // raised if a poller gave up waiting (never in correct operation)
     int budget;             // trips before parking; <= 0: never
     int max_backlog;        // parked fits waiting for a poller beyond which the main kernels stop parking
+    int on_demand_tail;     // != 0: the last wave of fits is claimed on demand, not ahead (IoDevice::stage)
     long long n_fits;
     int h, w;
     Options opt;
@@ -152,10 +153,20 @@ struct IoDevice {
         return __shfl_sync(ln.gmask, ok, src) != 0;
     }
 
-    // claim the next fit index for this group and start copying its inputs
-    __device__ void stage(const Lanes<G>& ln, int M, int stride) {
+    // Claim the next fit index for this group and start copying its inputs.  `after` is the index of the fit the group is
+    // about to work on (-1: none).  Near the end of the batch nothing is claimed ahead: a fit staged behind a long-running one
+    // would be stuck there while other groups have already run out of work, so the last wave is handed out on demand
+    // (fetch() then claims and loads synchronously).
+    __device__ void stage(const Lanes<G>& ln, int M, int stride, long long after) {
         constexpr int P = Mo::P;
         const int src = __ffs(ln.gmask) - 1;
+        const long long groups = (long long)gridDim.x * kWarps * (32 / G);
+        if (a.on_demand_tail && after >= 0 && after + 3 * groups >= a.n_fits) {
+            unsigned long long c = 0;
+            if (ln.lane == 0) c = *reinterpret_cast<volatile unsigned long long*>(a.counter);
+            c = __shfl_sync(ln.gmask, c, src);
+            if ((long long)c + groups >= a.n_fits) { next = -1; return; }
+        }
         unsigned long long idx = 0;
         if (ln.lane == 0) idx = atomicAdd(a.counter, 1ull);
         idx = __shfl_sync(ln.gmask, idx, src);
@@ -251,8 +262,8 @@ struct IoDevice {
         constexpr int P = Mo::P;
         if (RESUME) return fetch_parked(ln, px, st, fit);
         float pstart[P];
-        if (next < 0) stage(ln, px.M, px.stride);
         for (;;) {
+            if (next < 0) stage(ln, px.M, px.stride, -1);  // nothing staged (first fit, or the last wave): claim now
             if (next >= a.n_fits) {
                 // No new fits are left, only the ones in flight: from here on a kernel launched behind this one with the
                 // programmatic-serialization attribute (the lm() kernel behind the pre-fit kernel) may take the CTA slots
@@ -264,7 +275,7 @@ struct IoDevice {
             cp_async_wait_all();
             __syncwarp(ln.gmask);
             float* t = px.y; px.y = ynext; ynext = t;  // the staged buffer becomes the working one
-            stage(ln, px.M, px.stride);                 // and the following fit starts loading
+            stage(ln, px.M, px.stride, idx);            // and the following fit starts loading
 #pragma unroll
             for (int k = 0; k < P; ++k) pstart[k] = px.y[px.stride + k];
             if (MAIN) {
@@ -609,6 +620,7 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     const ParkQueue none{nullptr, nullptr, nullptr, nullptr, 0};
     KArgs a = a0;
     a.counter = counters;
+    a.on_demand_tail = getenv("DPHLM_NO_ON_DEMAND_TAIL") ? 0 : 1;  // tuning aid
     a.produce = a.consume[0] = a.consume[1] = none;
     a.wait_done[0] = a.wait_done[1] = nullptr;
     a.exit_counter = a.done_flag = nullptr;
