@@ -248,6 +248,7 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     template <class T> struct Geo { T dx, dy, r2; };
     template <class T> struct Diff { T dot, dr2, r20; };
     static constexpr int kTable = 0;
+    static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
     DPH_HD static int table_floats(int, int) { return 0; }
     template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
@@ -300,6 +301,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     template <class T> struct Geo { T dx, dy, u, v; };
     template <class T> struct Diff { T dx, dy, u, v; };
     static constexpr int kTable = 0;
+    static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
     DPH_HD static int table_floats(int, int) { return 0; }
     template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
@@ -389,14 +391,16 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
 // shared memory, for every axis position
 //   A = (E_b, dE_b/dc, dE_b/dsigma, E_b - E_a)   at the trial point b,     B = (E_a, J_axis(a) . d)   at the accepted point a,
 // and the pixel loop only gathers and multiplies.  The axis difference E_b - E_a uses the step difference any function
-// with a derivative can use: for small steps E(x + d) - E(x) = E'(x + d/2) d + O(d^3) (midpoint rule; relative error
-// ~ (d/scale)^2 / 24), for large steps the direct difference; the switch sits where both have the same absolute error.
+// with a derivative can use: for small steps E(x + d) - E(x) = (E'(x) + E'(x + d)) d / 2 + O(d^3) (trapezoid rule on the
+// derivatives both points need anyway; relative error ~ (d/scale)^2 / 12), for large steps the direct difference; the
+// switch sits where both have the same absolute error in fp32 (~1e-5 of the difference).
 // Then  f_b - f_a = d_amp E_bx E_by + amp_a (dEx E_by + E_ax dEy) + d_off  without cancellation.
 template <bool FIXED>
 struct Gauss2DIntegratedT {
-    static constexpr int P = FIXED ? 4 : 5, NE = 1, kMinCtas = 2, kOff = P - 1;
+    static constexpr int P = FIXED ? 4 : 5, NE = 1, kMinCtas = 3, kOff = P - 1;
     static constexpr int kAxisMax = 32;                // ROI side limit (validated by the entry points)
     static constexpr int kTable = 6 * 2 * kAxisMax;    // static bound, used by the covariance kernel
+    static constexpr bool kStoreE = false;             // the accepted point's pixel value is E_ax E_ay from the tables
     DPH_HD static int table_floats(int h, int w) { return (6 * (h + w) + 3) & ~3; }
     struct Par {
         float amp, x0, y0, sig = 1.0f, off, a = 0.70710678118654752f, c = 0.39894228040143268f, cs = 0.39894228040143268f;
@@ -404,7 +408,7 @@ struct Gauss2DIntegratedT {
         float w = 0.0f;              // ROI width: rows follow the columns in the tables
         int n = 0;                   // w + h
     };
-    struct Step { float d[P]; Par mid; bool direct; };
+    struct Step { float d[P]; bool direct; };
     template <class T> struct Geo { T ex, ey, dex, dey, sex, sey, dEx, dEy, exa, eya, ux, uy; };
     template <class T> struct Diff { T dEx, dEy, exa, eya, eyb, ux, uy; };
     DPH_HD static void set_sigma(Par& q, float sig) {
@@ -441,11 +445,11 @@ struct Gauss2DIntegratedT {
             const bool row = t >= w;
             const float pos = float(row ? t - w : t);
             const float dc = row ? st.d[2] : st.d[1], ds = FIXED ? 0.0f : st.d[FIXED ? 0 : 3];
-            float ea, dea, sea, eb, deb, seb, em, dem, sem;
+            float ea, dea, sea, eb, deb, seb;
             axis(q0, pos - (row ? q0.y0 : q0.x0), ea, dea, sea);
             axis(q1, pos - (row ? q1.y0 : q1.x0), eb, deb, seb);
-            axis(st.mid, pos - (row ? st.mid.y0 : st.mid.x0), em, dem, sem);
-            const float dE = st.direct ? eb - ea : f_fma(dem, dc, sem * ds);
+            // small step: trapezoid rule on the derivatives at both ends, which are needed anyway
+            const float dE = st.direct ? eb - ea : 0.5f * f_fma(dea + deb, dc, (sea + seb) * ds);
             A[t] = quad{eb, deb, seb, dE};
             B[t] = duo{ea, f_fma(dea, dc, sea * ds)};
         }
@@ -460,6 +464,7 @@ struct Gauss2DIntegratedT {
         g.exa = cb.a; g.ux = cb.b; g.eya = rb.a; g.uy = rb.b;
     }
     template <class T> DPH_HD static void expo(const Par&, const Geo<T>& g, T* e) { e[0] = g.ex * g.ey; }
+    template <class T> DPH_HD static void expo_old(const Geo<T>& g, T* e) { e[0] = g.exa * g.eya; }  // at the accepted point
     template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
     template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
         J[0] = e[0];
@@ -469,18 +474,12 @@ struct Gauss2DIntegratedT {
         J[kOff] = T(1.0f);
     }
     DPH_HD static void prepare_step(const Par& a, const Par&, const float* d, Step& s) {
-        float pm[P];
-        pm[0] = a.amp + 0.5f * d[0]; pm[1] = a.x0 + 0.5f * d[1]; pm[2] = a.y0 + 0.5f * d[2];
-        if (!FIXED) pm[3] = a.sig + 0.5f * d[3];
-        pm[kOff] = a.off + 0.5f * d[kOff];
 #pragma unroll
         for (int k = 0; k < P; ++k) s.d[k] = d[k];
-        s.mid = a;
-        prepare(pm, s.mid);
         const float is = f_rcp(fabsf(a.sig));
         float rel = fmaxf(fabsf(d[1]), fabsf(d[2])) * is;
         if (!FIXED) rel = fmaxf(rel, fabsf(d[3]) * is);
-        s.direct = !(rel <= 0.015625f);
+        s.direct = !(rel <= 0.011f);
     }
     template <class T> DPH_HD static void diff(const Par&, const Step&, const Geo<T>& g1, Diff<T>& df) {
         df.dEx = g1.dEx; df.dEy = g1.dEy; df.exa = g1.exa; df.eya = g1.eya; df.eyb = g1.ey; df.ux = g1.ux; df.uy = g1.uy;
@@ -506,6 +505,7 @@ struct MultiExp {
     template <class T> struct Geo { T x; };
     template <class T> struct Diff { T x; };
     static constexpr int kTable = 0;
+    static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
     DPH_HD static int table_floats(int, int) { return 0; }
     template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
@@ -570,6 +570,7 @@ template <int NEXP, bool OFFSET>
 struct MultiExpIrf {
     static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = 2 * NEXP, kMinCtas = 2;
     static constexpr int kTable = 2 * NEXP * kIrfTaps;
+    static constexpr bool kStoreE = true;
     DPH_HD static int table_floats(int, int) { return kTable; }
     static constexpr float kTrapz = 0.009f;  // |dk u| below which the trapezoid rule beats the direct difference in fp32
     struct Par {
@@ -814,8 +815,12 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
     T e0[NE], J[P];
     Mo::geometry(q1, cx, cy, g1);
     Mo::expo(q1, g1, e1);
+    if constexpr (Mo::kStoreE) {
 #pragma unroll
-    for (int j = 0; j < NE; ++j) e0[j] = v_pick(init, e1[j], e0in[j]);
+        for (int j = 0; j < NE; ++j) e0[j] = v_pick(init, e1[j], e0in[j]);
+    } else {
+        Mo::expo_old(g1, e0);  // on the first pass the tables of the accepted point equal the trial ones
+    }
     Mo::diff(q0, st, g1, df);
     const T f0 = Mo::value(q0, e0);
     const T f1 = Mo::value(q1, e1);
@@ -877,14 +882,18 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
         for (int q = ln.lane; q < npair; q += G) {
             const int i = 2 * q;
             f2 e0[NE], e1[NE];
+            if constexpr (Mo::kStoreE) {
 #pragma unroll
-            for (int j = 0; j < NE; ++j) e0[j] = *reinterpret_cast<const f2*>(e0b + j * stride + i);
+                for (int j = 0; j < NE; ++j) e0[j] = *reinterpret_cast<const f2*>(e0b + j * stride + i);
+            }
             const f2 cx = *reinterpret_cast<const f2*>(px.cx + i);
             const f2 cy = *reinterpret_cast<const f2*>(px.cy + i);
             const f2 y = *reinterpret_cast<const f2*>(px.y + i);
             pixel_regular<Mo, MLE, PRED, f2>(q0, q1, st, init, want_chi, cx, cy, y, e0, e1, a2);
+            if constexpr (Mo::kStoreE) {
 #pragma unroll
-            for (int j = 0; j < NE; ++j) *reinterpret_cast<f2*>(e1b + j * stride + i) = e1[j];
+                for (int j = 0; j < NE; ++j) *reinterpret_cast<f2*>(e1b + j * stride + i) = e1[j];
+            }
         }
         Acc<P, float> a1;
 #pragma unroll
@@ -896,11 +905,15 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
         if ((px.M & 1) && ln.lane == npair % G) {  // odd pixel count: the last pixel alone
             const int i = px.M - 1;
             float e0[NE], e1[NE];
+            if constexpr (Mo::kStoreE) {
 #pragma unroll
-            for (int j = 0; j < NE; ++j) e0[j] = e0b[j * stride + i];
+                for (int j = 0; j < NE; ++j) e0[j] = e0b[j * stride + i];
+            }
             pixel_regular<Mo, MLE, PRED, float>(q0, q1, st, init, want_chi, px.cx[i], px.cy[i], px.y[i], e0, e1, a1);
+            if constexpr (Mo::kStoreE) {
 #pragma unroll
-            for (int j = 0; j < NE; ++j) e1b[j * stride + i] = e1[j];
+                for (int j = 0; j < NE; ++j) e1b[j * stride + i] = e1[j];
+            }
         }
 #pragma unroll
         for (int k = 0; k < NT<P>::value; ++k) n.A[k] = a1.A[k];
@@ -917,11 +930,15 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
             float e0[NE], e1[NE], J[P];
             Mo::geometry(q1, px.cx[i], px.cy[i], g1);
             Mo::expo(q1, g1, e1);
+            if constexpr (Mo::kStoreE) {
 #pragma unroll
-            for (int j = 0; j < NE; ++j) {
-                float t = e0b[j * stride + i];
-                e0[j] = init ? e1[j] : t;
-                e1b[j * stride + i] = e1[j];
+                for (int j = 0; j < NE; ++j) {
+                    float t = e0b[j * stride + i];
+                    e0[j] = init ? e1[j] : t;
+                    e1b[j * stride + i] = e1[j];
+                }
+            } else {
+                Mo::expo_old(g1, e0);
             }
             const float y = px.y[i];
             Mo::diff(q0, st, g1, df);

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G;
     const int table = Mo::table_floats(a.h, a.w);
-    const int region = group_region(stride, Mo::NE, table);
+    const int region = group_region(stride, Mo::kStoreE ? Mo::NE : 0, table);
     float* base = smem + 2 * ((M + 1) & ~1) + (warp * FPW + grp) * region;
     Lanes<G> ln{lane % G, G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G))};
     PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cx, cy, M, stride, 0};
@@ -610,8 +610,8 @@ template <class Mo, bool MLE, int G>
 int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t stream) {
     const int M = a0.h * a0.w;
     constexpr int FPW = 32 / G;
-    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::NE, Mo::table_floats(a0.h, a0.w)));
-    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::NE, Mo::table_floats(a0.h, a0.w)));
+    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w)));
+    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w)));
     const bool handoff = G < 32 && pl.cap > 0;
     const int kPollerCtas = budget_from_env("DPHLM_POLLER_CTAS", kPollerCtasDefault);  // tuning aid
     using SA = StageA<Mo>;
