@@ -250,7 +250,7 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     static constexpr int kTable = 0;
     static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
+    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
@@ -303,7 +303,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     static constexpr int kTable = 0;
     static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
+    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];
@@ -399,14 +399,14 @@ template <bool FIXED>
 struct Gauss2DIntegratedT {
     static constexpr int P = FIXED ? 4 : 5, NE = 1, kMinCtas = 3, kOff = P - 1;
     static constexpr int kAxisMax = 32;                // ROI side limit (validated by the entry points)
-    static constexpr int kTable = 6 * 2 * kAxisMax;    // static bound, used by the covariance kernel
+    static constexpr int kTable = 10 * 2 * kAxisMax;   // static bound, used by the covariance kernel
     static constexpr bool kStoreE = false;             // the accepted point's pixel value is E_ax E_ay from the tables
-    DPH_HD static int table_floats(int h, int w) { return (6 * (h + w) + 3) & ~3; }
+    DPH_HD static int table_floats(int h, int w) { return (10 * (h + w) + 3) & ~3; }
     struct Par {
         float amp, x0, y0, sig = 1.0f, off, a = 0.70710678118654752f, c = 0.39894228040143268f, cs = 0.39894228040143268f;
-        const float* tbl = nullptr;  // tables of the trial point this Par describes (fill_tables)
-        float w = 0.0f;              // ROI width: rows follow the columns in the tables
-        int n = 0;                   // w + h
+        const float* tbl = nullptr;   // axis table of the trial point this Par describes (fill_tables)
+        const float* tblb = nullptr;  // (E_accepted, J_axis . d) pairs
+        float w = 0.0f;               // ROI width: rows follow the columns in the tables
     };
     struct Step { float d[P]; bool direct; };
     template <class T> struct Geo { T ex, ey, dex, dey, sex, sey, dEx, dEy, exa, eya, ux, uy; };
@@ -435,22 +435,33 @@ struct Gauss2DIntegratedT {
         de = (gm - gp) * q.c;
         se = (tm * gm - tp * gp) * q.cs;
     }
-    template <class L> DPH_HD static void fill_tables(const L& ln, const Par& q0, Par& q1, Step& st, float* tbl, int h, int w) {
-        const int n = h + w;
-        q1.tbl = tbl; q1.w = float(w); q1.n = n;
-        quad* A = reinterpret_cast<quad*>(tbl);
-        duo* B = reinterpret_cast<duo*>(tbl + 4 * n);
+    // Tables: two buffers of (E, dE/dc, dE/dsigma, E - E_accepted) per axis position -- the accepted point and the trial point;
+    // accepting a step flips which is which (phase bit 0, the same index as the per-pixel buffers of the other models), so
+    // every trip evaluates the axis integrals at ONE point -- and a (E_accepted, J_axis(accepted) . d) pair per position.
+    template <class L> DPH_HD static void fill_tables(const L& ln, const Par& q0, Par& q1, Step& st, float* tbl, int h, int w, int phase) {
+        const int n = h + w, cur = phase & 1;
+        const bool init = phase & 2;
+        quad* acc = reinterpret_cast<quad*>(tbl) + (cur ? n : 0);
+        quad* trial = reinterpret_cast<quad*>(tbl) + (cur ? 0 : n);
+        duo* B = reinterpret_cast<duo*>(tbl + 8 * n);
+        q1.tbl = reinterpret_cast<const float*>(trial); q1.tblb = reinterpret_cast<const float*>(B); q1.w = float(w);
         ln.sync();  // the previous pass has finished reading the tables
         for (int t = ln.lane; t < n; t += L::kLanes) {
             const bool row = t >= w;
             const float pos = float(row ? t - w : t);
             const float dc = row ? st.d[2] : st.d[1], ds = FIXED ? 0.0f : st.d[FIXED ? 0 : 3];
             float ea, dea, sea, eb, deb, seb;
-            axis(q0, pos - (row ? q0.y0 : q0.x0), ea, dea, sea);
             axis(q1, pos - (row ? q1.y0 : q1.x0), eb, deb, seb);
+            if (init) {  // first pass of a fit (fresh or resumed): accepted point = trial point, zero step
+                ea = eb; dea = deb; sea = seb;
+                acc[t] = quad{ea, dea, sea, 0.0f};
+            } else {
+                const quad a = acc[t];
+                ea = a.x; dea = a.y; sea = a.z;
+            }
             // small step: trapezoid rule on the derivatives at both ends, which are needed anyway
             const float dE = st.direct ? eb - ea : 0.5f * f_fma(dea + deb, dc, (sea + seb) * ds);
-            A[t] = quad{eb, deb, seb, dE};
+            trial[t] = quad{eb, deb, seb, dE};
             B[t] = duo{ea, f_fma(dea, dc, sea * ds)};
         }
         ln.sync();
@@ -458,7 +469,7 @@ struct Gauss2DIntegratedT {
     template <class T> DPH_HD static void geometry(const Par& q, T cx, T cy, Geo<T>& g) {
         const T r = cy + T(q.w);
         const Q4<T> ca = v_gather4(q.tbl, cx), ra = v_gather4(q.tbl, r);
-        const Q2<T> cb = v_gather2(q.tbl + 4 * q.n, cx), rb = v_gather2(q.tbl + 4 * q.n, r);
+        const Q2<T> cb = v_gather2(q.tblb, cx), rb = v_gather2(q.tblb, r);
         g.ex = ca.a; g.dex = ca.b; g.sex = ca.c; g.dEx = ca.d;
         g.ey = ra.a; g.dey = ra.b; g.sey = ra.c; g.dEy = ra.d;
         g.exa = cb.a; g.ux = cb.b; g.eya = rb.a; g.uy = rb.b;
@@ -507,7 +518,7 @@ struct MultiExp {
     static constexpr int kTable = 0;
     static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int) {}
+    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
 #pragma unroll
@@ -594,7 +605,7 @@ struct MultiExpIrf {
         q.off = OFFSET ? p[2 * NEXP] : 0.0f;
     }
     // prefix sums S, T over the IRF taps for every exponential of the point q, by the lanes of the group
-    template <class L> DPH_HD static void fill_tables(const L& ln, const Par&, Par& q, Step&, float* tbl, int, int) {
+    template <class L> DPH_HD static void fill_tables(const L& ln, const Par&, Par& q, Step&, float* tbl, int, int, int) {
         q.tbl = tbl;
         if (!q.consts) return;  // idle group
         constexpr int G = L::kLanes;
@@ -1401,7 +1412,8 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         q1 = st.q0;  // carries the constants of the call (fixed-width model)
         Mo::prepare(xn, q1);
         Mo::prepare_step(st.q0, q1, p, step);
-        Mo::fill_tables(ln, st.q0, q1, step, px.tbl, px.M / px.w, px.w);  // models with per-trial tables; no-op otherwise
+        // models with per-trial tables; no-op otherwise.  Last argument: bit 0 = which buffer holds the accepted point, bit 1 = first pass
+        Mo::fill_tables(ln, st.q0, q1, step, px.tbl, px.M / px.w, px.w, px.cur | (st.init ? 2 : 0));
         const bool init = st.init, want_chi = Lanes<G>::warp_any(pass && st.wants_chi());
         trial_pass<Mo, Stage::kMle, Stage::kPred, true, G>(ln, px, st.q0, q1, step, init, want_chi, nrm);
         if (Stage::kMle && Lanes<G>::warp_any(pass && (nrm.flags & kFlagIrregular))) {

@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(128) dphlm_cov_kernel(const CovArgs a) {
         typename Mo::Step st;
         Mo::prepare_step(q, q, zero, st);
         const typename Mo::Par q0 = q;
-        Mo::fill_tables(ln, q0, q, st, tables + (threadIdx.x / G) * Mo::kTable, a.h, a.w);
+        Mo::fill_tables(ln, q0, q, st, tables + (threadIdx.x / G) * Mo::kTable, a.h, a.w, 2);  // first pass, buffer 0
     }
     Acc<P, float> acc;
     acc.clear();
