@@ -148,6 +148,18 @@ DPH_HD T log1p_acc(T u) {
     T big = v_lg2(v_max(u + T(1.0f), 1e-37f)) * T(kLn2);
     return v_sel_small(u, kLog1pSmall, p, big);
 }
+// the same for callers that use the result only when 1 + u > 0 is known (the branch-free pass): no clamp
+template <class T>
+DPH_HD T log1p_pos(T u) {
+    T p = T(-1.0f / 6.0f);
+    p = f_fma(p, u, T(0.2f));
+    p = f_fma(p, u, T(-0.25f));
+    p = f_fma(p, u, T(1.0f / 3.0f));
+    p = f_fma(p, u, T(-0.5f));
+    p = f_fma(p * u, u, u);
+    T big = v_lg2(u + T(1.0f)) * T(kLn2);
+    return v_sel_small(u, kLog1pSmall, p, big);
+}
 
 // expm1(a) for |a| <= 1/16 (Taylor, degree 5, truncation < 2e-9 relative); callers handle larger |a| by
 // direct differences of the stored exponentials.
@@ -838,14 +850,17 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
     const T dl = Mo::delta(q0, st, df, e0, e1);
     Mo::jac(q1, g1, e1, J);
     if (MLE) {
+        // The sums of this pass are used only if every model value involved is positive: the old one (the driver repeats the
+        // pass in the literal form whenever the accepted point had a non-positive pixel), the trial one and the predicted one
+        // (tracked in n.lo; the clamp turns a NaN into a 0 that the minimum sees).  So 1 + u = f_new / f_old > 0 where it counts.
         const T f1c = v_max(f1, 0.0f);
-        const T rf0 = v_rcp(v_max(f0, 0.0f));
-        n.actual = f_fma(y, log1p_acc(dl * rf0), n.actual) - dl;
+        const T rf0 = v_rcp(f0);
+        n.actual = f_fma(y, log1p_pos(dl * rf0), n.actual) - dl;
         if (PRED) {
             const T jd = Mo::jdx(q0, st, df, e0);
             const T dp = dl + jd;
-            n.lo = v_min3(n.lo, f1c, f1c + jd);  // f_old was a trial value itself and was checked then
-            n.predicted = f_fma(y, log1p_acc(dp * rf0), n.predicted) - dp;
+            n.lo = v_min3(n.lo, f1c, f1c + jd);
+            n.predicted = f_fma(y, log1p_pos(dp * rf0), n.predicted) - dp;
         } else {
             n.lo = v_min3(n.lo, f1c, f1c);
         }
@@ -1380,6 +1395,7 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
     typename Mo::Par q1;
     typename Mo::Step step;
     bool has = false, exhausted = false;
+    bool old_irregular = false;  // the accepted point of this group's fit has a non-positive (or non-finite) model value
     long long fit = -1;
 #pragma unroll
     for (int i = 0; i < P; ++i) p[i] = 1.0f;
@@ -1416,15 +1432,19 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         Mo::fill_tables(ln, st.q0, q1, step, px.tbl, px.M / px.w, px.w, px.cur | (st.init ? 2 : 0));
         const bool init = st.init, want_chi = Lanes<G>::warp_any(pass && st.wants_chi());
         trial_pass<Mo, Stage::kMle, Stage::kPred, true, G>(ln, px, st.q0, q1, step, init, want_chi, nrm);
-        if (Stage::kMle && Lanes<G>::warp_any(pass && (nrm.flags & kFlagIrregular))) {
+        // the branch-free pass is valid only between two regular points; otherwise repeat it in the literal form
+        const bool trial_irregular = Stage::kMle && (nrm.flags & kFlagIrregular);
+        const bool literal = Stage::kMle && (trial_irregular || (old_irregular && !init));
+        if (Stage::kMle && Lanes<G>::warp_any(pass && literal)) {
             Normal<P> slow;
             trial_pass<Mo, Stage::kMle, Stage::kPred, false, G>(ln, px, st.q0, q1, step, init, want_chi, slow);
-            if (nrm.flags & kFlagIrregular) nrm = slow;
+            if (literal) nrm = slow;
         }
         if (pass) {
             bool accepted;
             const bool done = st.consume(opt, nrm, p, q1, accepted);
             if (accepted) px.cur = 1 - px.cur;
+            if (accepted || init) old_irregular = trial_irregular;  // the first pass evaluates the accepted point itself
             if (done) {
                 io.store(ln, st, fit);
                 has = false;

@@ -305,3 +305,16 @@ def test_uint16_camera_counts_equal_float32(golden):
     b = dph.curve_fit_batch(models.gauss2d, g["data"][:3000].astype(np.uint16), g["p0"][:3000], "mle")
     np.testing.assert_array_equal(a.popt, b.popt)
     np.testing.assert_array_equal(a.info, b.info)
+
+
+def test_model_crossing_zero_on_gpu():
+    """Fits whose model goes non-positive at accepted points (negative fitted offsets): the CUDA path against the float64 oracle."""
+    from dphtools_b200 import synth
+
+    w = synth.gauss2d_rois(400, 11, seed=77, photons=(60.0, 400.0), bg=(0.0, 0.25))
+    ref = lm_oracle.fit_batch(models.gauss2d, w["data"], w["p0"], "mle", models.roi_grid(11, 11))
+    for lanes in (0, 32):
+        r = dph.curve_fit_batch(models.gauss2d, torch.from_numpy(w["data"]).cuda(), torch.from_numpy(w["p0"]).cuda(), "mle", group_lanes=lanes)
+        out = dict(popt=r.popt.cpu().numpy(), info=r.info.cpu().numpy(), nfev=r.nfev.cpu().numpy())
+        rep = parity_report("gauss2d", out, ref)
+        assert rep["converged_equal"] == 1.0 and rep["within_rtol"] == 1.0 and rep["info_equal"] >= 0.99, rep

@@ -51,3 +51,19 @@ def test_keywords_reach_both_stages_like_the_reference(golden, kw):
     rel = np.abs(out["popt"][both][:, :4] - ref["popt"][both][:, :4]) / np.abs(ref["popt"][both][:, :4])
     assert np.quantile(rel.max(1), 0.99) < 1e-4
     assert (np.sign(out["info"][~conv_o]) == np.sign(ref["info"][~conv_o])).all()  # pre-fit failure vs lm() failure
+
+
+def test_model_crossing_zero_matches_the_reference_clamps():
+    """Dim spots on almost no background: one fit in six ends with a negative offset, so the model is non-positive at some
+    pixels of accepted points and the literal path with the reference's clamps and zeroing rules (lm.py:84-103, 124-132)
+    has to take over from the branch-free one, also for the trip that leaves such a point."""
+    from dphtools_b200 import synth
+    from oracle import lm_oracle
+
+    w = synth.gauss2d_rois(400, 11, seed=77, photons=(60.0, 400.0), bg=(0.0, 0.25))
+    ref = lm_oracle.fit_batch(models.gauss2d, w["data"], w["p0"], "mle", models.roi_grid(11, 11))
+    assert (ref["popt"][:, 4] < 0).sum() > 30
+    for budget in (0, 4):
+        out = host_emu.fit_batch(0, "mle", w["data"], w["p0"], None, budget=budget)
+        rep = parity_report("gauss2d", out, ref)
+        assert rep["converged_equal"] == 1.0 and rep["within_rtol"] == 1.0 and rep["info_equal"] >= 0.99, rep
