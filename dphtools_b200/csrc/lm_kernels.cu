@@ -64,6 +64,7 @@ int auto_group(int M) {
 int validate_shape(const dphlm_desc* d) {
     if (!d) return fail("null descriptor");
     if (d->n_fits < 0) return fail("n_fits < 0");
+    if (d->n_fits > 2000000000LL) return fail("n_fits above 2e9 per call: split the batch");  // straggler lists hold 32-bit fit indices
     if (d->dim0 < 1 || d->dim1 < 1) return fail("dim0/dim1 must be >= 1");
     switch (d->model) {
         case DPHLM_GAUSS2D:
@@ -102,6 +103,7 @@ int validate_shape(const dphlm_desc* d) {
 int validate(const dphlm_desc* d) {
     if (!d) return fail("null descriptor");
     if (d->n_fits < 0) return fail("n_fits < 0");
+    if (d->n_fits > 2000000000LL) return fail("n_fits above 2e9 per call: split the batch");  // straggler lists hold 32-bit fit indices
     if (d->dim0 < 1 || d->dim1 < 1) return fail("dim0/dim1 must be >= 1");
     if (d->method != DPHLM_LS && d->method != DPHLM_MLE) return fail("Method not recognized");
     if (d->n_fits > 0 && (!d->data || !d->p0 || !d->popt || !d->info || !d->nfev || !d->chisq))
