@@ -51,6 +51,8 @@ CASES = [
     (lambda: models.gauss2d_integrated, 7, 7, 1000, 2),
     (lambda: models.gauss2d_integrated_fixed(1.15), 8, 11, 300, 4),
     (lambda: models.gauss2d_integrated_fixed(1.15), 11, 8, 14300, 0),   # a little more than one wave of 4-lane groups
+    (lambda: models.gauss2d, 25, 25, 200, 0),
+    (lambda: models.gauss2d_integrated, 31, 29, 100, 0),
 ]
 
 
@@ -78,3 +80,27 @@ def test_odd_shapes_match_the_host_build(case):
         assert np.quantile(rel.max(1), 0.99) < 1e-4, (case, host, np.quantile(rel.max(1), 0.99))
         # (the fixed-width model converges quadratically and ends with ftol and xtol both borderline: more 1 <-> 2 swaps)
         assert (got["info"] == ref["info"]).mean() >= (0.93 if fixed else 0.97), (case, host)
+
+
+def test_long_histograms_and_wide_rois():
+    """1024-bin decays (16 and 32 lanes per fit) and a 32x32 ROI are within the shared-memory layout; a 100x100 ROI is refused
+    with an error instead of a bad launch."""
+    rng = np.random.default_rng(5)
+    x = (0.0125 * np.arange(1024)).astype(np.float32)
+    truth = np.stack([rng.uniform(200, 2000, 64), rng.uniform(1.5, 3.0, 64), rng.uniform(100, 1000, 64), rng.uniform(0.2, 0.6, 64),
+                      rng.uniform(1, 10, 64)], 1)
+    xd = x[None, :].astype(float)
+    mu = truth[:, 0:1] * np.exp(-truth[:, 1:2] * xd) + truth[:, 2:3] * np.exp(-truth[:, 3:4] * xd) + truth[:, 4:5]
+    data = rng.poisson(mu).astype(np.float32)
+    p0 = (truth * rng.uniform(0.8, 1.2, truth.shape)).astype(np.float32)
+    ref = host_emu.fit_batch(models.multi_exp.model_id, "mle", data, p0, x)
+    for lanes in (16, 32):
+        r = dph.curve_fit_batch(models.multi_exp, data, p0, "mle", x, group_lanes=lanes)
+        ok = (r.info >= 1) & (r.info <= 4) & (ref["info"] >= 1) & (ref["info"] <= 4)
+        assert ok.mean() > 0.9
+        assert np.quantile(np.abs(r.popt[ok] - ref["popt"][ok]) / np.abs(ref["popt"][ok]), 0.99) < 1e-4
+    big, p0b = _spots(models.gauss2d, 32, 32, 40, seed=9)
+    r = dph.curve_fit_batch(models.gauss2d, big, p0b, "mle")
+    assert ((r.info >= 1) & (r.info <= 4)).mean() > 0.9
+    with pytest.raises(RuntimeError, match="too large|ROI"):
+        dph.curve_fit_batch(models.gauss2d, np.ones((4, 100, 100), np.float32), np.ones((4, 5), np.float32), "mle", group_lanes=4)
