@@ -1,15 +1,18 @@
 // lm_launch.cuh -- kernel template and launcher shared by the per-model translation units.
 //
-// Execution model.  One fit is owned by a group of G lanes of a warp (G = 2, 4, 8, 16 or 32, so a warp
-// carries 32/G fits).  Warps are persistent: each one pulls the next batch of 32/G consecutive fits from
-// a global atomic counter, stages their ROIs into its private slice of shared memory with coalesced
-// loads (clamping to >= 0 for the MLE estimator, lm.py:127, and checking finiteness, lm.py:651-652),
-// runs both stages of the fit (lm_core.cuh: fit_one) and writes popt / info / nfev / chisq.  There is no
-// CTA-level synchronisation after the coordinate table is built: warps never wait for each other, which
-// is what absorbs the 6..30+ spread in iteration counts between fits.
+// Execution model.  One fit is owned by a group of G lanes of a warp (G = 2, 4, 8, 16 or 32, so a warp carries 32/G fits).
+// Each stage of curve_fit(method='ls'|'mle') is one persistent kernel (dphlm_stage_kernel<StageA|StageB, Model, G, IO>):
+// every lane group pulls its next fit from a global atomic counter as soon as its current one ends, stages the ROI into its
+// own slice of shared memory with cp.async while the current fit iterates (clamping to >= 0 for the MLE estimator,
+// lm.py:127, and checking finiteness, lm.py:651-652), runs lm_core.cuh: run_stage and writes its results.  There is no
+// CTA-level synchronisation after the coordinate tables are built: groups never wait for each other, which is what absorbs
+// the 6..30+ spread in iteration counts between fits.  Fits beyond the trip budget are parked in a
+// queue and finished by a concurrently running poller kernel with a whole warp per fit; the lm() kernel is launched so that
+// it starts in the CTA slots the pre-fit kernel frees while it drains (see launch()).
 //
-// Shared memory per warp: (32/G) * M * (1 + 2*NE) floats -- the data y and the double-buffered stored
-// exponentials of the accepted and the trial point (accepting a step flips a buffer index).
+// Shared memory per lane group: two data buffers (the working ROI and the staged next one, each followed by the staged
+// start parameters and pre-fit exit code), the double-buffered per-pixel values of the accepted and the trial point for
+// models that keep them (accepting a step flips a buffer index), and the per-trial tables of models that have them.
 #pragma once
 #include <cuda_runtime.h>
 
