@@ -42,6 +42,9 @@ SETS = {
     "c6_mle": ("c6_gauss2d_int_11", 2000, 6, "mle"),
     "c7_mle": ("c7_gauss2d_intf_11", 2000, 7, "mle"),
     "c8_mle": ("c8_multiexp_irf_256", 1000, 8, "mle"),
+    "c6_ls": ("c6_gauss2d_int_11", 1000, 16, "ls"),
+    "c7_ls": ("c7_gauss2d_intf_11", 1000, 17, "ls"),
+    "c8_ls": ("c8_multiexp_irf_256", 500, 18, "ls"),
 }
 MODEL_OF = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp, "c6": models.gauss2d_integrated,
             "c7": models.gauss2d_integrated_fixed(1.3), "c8": models.multi_exp_convolved([1.0], 1.0)}

@@ -16,7 +16,7 @@ torch = pytest.importorskip("torch")
 CASES = [
     ("c1_mle", 0.99, 1.0), ("c2_mle", 0.995, 1.0), ("c2_ls", 0.99, 1.0), ("c3_mle", 0.995, 0.999),
     ("c4_mle", 0.995, 1.0), ("c4_ls", 0.995, 1.0), ("c5_mle", 0.995, 1.0), ("c5_ls", 0.995, 1.0), ("c6_mle", 0.99, 1.0),
-    ("c8_mle", 0.99, 1.0),
+    ("c8_mle", 0.99, 1.0), ("c6_ls", 0.99, 1.0), ("c7_ls", 0.99, 1.0), ("c8_ls", 0.99, 1.0),
     ("c7_mle", 0.97, 1.0),  # fixed width: quadratic convergence ends with ftol and xtol both borderline -> more 1<->2 swaps
 ]
 
@@ -111,6 +111,29 @@ def test_full_size_statistical_properties():
     ref = lm_oracle.fit_batch(models.gauss2d, w["data"][:n], w["p0"][:n], "mle", models.roi_grid(11, 11))
     rep = parity_report("gauss2d", dict(popt=popt[:n], info=info[:n], nfev=r.nfev.cpu().numpy()[:n]), ref)
     assert rep["converged_equal"] == 1.0 and rep["within_rtol"] == 1.0, rep
+
+
+@pytest.mark.parametrize("workload,n", [("c6_gauss2d_int_11", 50000), ("c7_gauss2d_intf_11", 50000), ("c8_multiexp_irf_256", 10000)])
+def test_newer_models_recover_the_truth(workload, n):
+    """The pixel-integrated Gaussians and the IRF-convolved decay at batch size: convergence, unbiasedness against the
+    generating parameters, idempotence."""
+    w = synth.WORKLOADS[workload](n, seed=21)
+    name = {"c6": "gauss2d_integrated", "c7": "gauss2d_integrated_fixed", "c8": "multi_exp_convolved"}[workload[:2]]
+    model = models.resolve(name, w.get("consts"))
+    data, p0 = torch.from_numpy(w["data"]).cuda(), torch.from_numpy(w["p0"]).cuda()
+    r = dph.curve_fit_batch(model, data, p0, "mle", w["xaxis"])
+    info, popt = r.info.cpu().numpy(), r.popt.cpu().numpy().astype(float)
+    ok = (info >= 1) & (info <= 4)
+    assert ok.mean() > 0.999
+    err = (popt - w["truth"])[ok]
+    if workload[:2] in ("c6", "c7"):
+        assert np.abs(np.median(err[:, 1:3], axis=0)).max() < 3e-3          # unbiased centre
+        assert abs(np.median(err[:, 0] / w["truth"][ok, 0])) < 0.01         # photon count within 1 %
+    else:
+        assert abs(np.median(err[:, 3] / w["truth"][ok, 3])) < 0.01         # slow rate within 1 %
+    r2 = dph.curve_fit_batch(model, data, r.popt, "mle", w["xaxis"])
+    p2 = r2.popt.cpu().numpy().astype(float)
+    assert np.quantile(np.abs(p2[ok] - popt[ok]).max(1) / np.abs(popt[ok]).max(1), 0.999) < 1e-4
 
 
 def test_single_fit_curve_fit_surface(golden):

@@ -6,7 +6,7 @@ import pytest
 from dphtools_b200 import models
 from oracle import lm_oracle
 
-SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle", "c7_mle", "c8_mle"]
+SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle", "c7_mle", "c8_mle", "c6_ls", "c7_ls", "c8_ls"]
 
 
 def _xdata(g):
