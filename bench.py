@@ -253,19 +253,20 @@ def main():
 
     # ---- the two kernels alone: per-launch durations (CUDA events recorded by the library on the launch
     # stream around each kernel) and algorithmic flops from the per-fit counters the kernels return
-    t_pre, t_main, fl_pre, fl_main = [], [], [], []
+    t_pre, t_main, t_tail, fl_pre, fl_main = [], [], [], [], []
     for i in range(min(args.steps, 8)):
         torch.cuda.synchronize()
         r = dph.curve_fit_batch(models.gauss2d, d_data[i % N_SETS], d_p0[i % N_SETS], "mle", return_counts=True,
                                 group_lanes=args.group_lanes, timing=True)
-        ms_pre, ms_main = _lib.last_kernel_ms()
+        ms_pre, ms_main, ms_tail = _lib.last_kernel_ms()
         t_pre.append(ms_pre * 1e-3)
         t_main.append(ms_main * 1e-3)
+        t_tail.append(ms_tail * 1e-3)
         c = r.counts.sum(0).double().cpu().numpy()
         fl_pre.append(ROI * ROI * F_LS * c[0])
         fl_main.append(ROI * ROI * (F_0 * n + F_ACC * c[1] + F_REJ * c[2]))
-    k_pre, k_main = float(np.mean(t_pre)), float(np.mean(t_main))
-    k_s = k_pre + k_main
+    k_pre, k_main, k_tail = float(np.mean(t_pre)), float(np.mean(t_main)), float(np.mean(t_tail))
+    k_s = k_pre + k_main + k_tail  # the whole call: both main kernels and the wait for the pollers' last straggler
     flops = [a + b for a, b in zip(fl_pre, fl_main)]
     achieved_tf = float(np.mean(fl_main)) / k_main / 1e12      # dominant kernel: the lm() loop
     step_tf = float(np.mean(flops)) / k_s / 1e12               # both kernels of a step
@@ -345,8 +346,9 @@ def main():
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
                 # dram__bytes_read+write of the lm() main launch from the ncu --set full capture of this workload
                 # (profiles/r1_ncu_full_final_gauss2d_11x11_G4.txt); algorithmic: 484 B/fit read again + 32 B/fit written
-                "traffic": 51.2e6 * n / 1e5, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; with its straggler follow-up launches)",
+                "traffic": 51.2e6 * n / 1e5, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; the main launch, events around it)",
                 "kernel_ms": k_main * 1e3, "share_of_step": k_main / k_s,
+                "straggler_tail_ms": k_tail * 1e3,  # after the lm() kernel: the pollers finishing the longest straggler (mean over the input sets)
                 "peak_source": "SMs x 128 lanes x 2 x max SM clock (no fp32 entry in MEASURED_PEAKS.json)",
                 "flops_per_fit": float(np.mean(fl_main)) / n,
                 "prefit_kernel": {"kernel": "dphlm_stage_kernel<StageA<Gauss2D>> (MINPACK pre-fit, lm.py:642-648)", "kernel_ms": k_pre * 1e3,

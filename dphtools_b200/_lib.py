@@ -69,7 +69,7 @@ def lib():
         L.dphlm_host_free.argtypes = [ctypes.c_void_p]
         L.dphlm_host_free.restype = None
         L.dphlm_device_count.restype = ctypes.c_int
-        L.dphlm_last_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float * 2)]
+        L.dphlm_last_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float * 3)]
         L.dphlm_last_kernel_ms.restype = ctypes.c_int
         L.dphlm_version.restype = ctypes.c_int
         L.dphlm_last_error.restype = ctypes.c_char_p
@@ -83,11 +83,12 @@ FLAG_DATA_U16 = 4
 
 
 def last_kernel_ms():
-    """(pre-fit ms, lm() ms) of this thread's last timed device call; blocks until it has finished."""
-    ms = (ctypes.c_float * 2)()
+    """(pre-fit main kernel, lm() main kernel, straggler tail after it) in ms for this thread's last timed device call; blocks
+    until it has finished."""
+    ms = (ctypes.c_float * 3)()
     if lib().dphlm_last_kernel_ms(ctypes.byref(ms)) != 0:
         raise RuntimeError("dphlm: " + last_error())
-    return float(ms[0]), float(ms[1])
+    return float(ms[0]), float(ms[1]), float(ms[2])
 
 
 def last_error():

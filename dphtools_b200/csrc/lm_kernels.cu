@@ -23,7 +23,7 @@ namespace {
 DeviceCtx g_ctx[64];
 
 struct TimingEvents {
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool valid = false;
 };
 thread_local TimingEvents g_timing;
@@ -379,11 +379,12 @@ void dphlm_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
-int dphlm_last_kernel_ms(float ms[2]) {
+int dphlm_last_kernel_ms(float ms[3]) {
     if (!ms || !g_timing.valid) return fail("no timed dphlm_fit_batch call on this thread");
-    CUDA_TRY(cudaEventSynchronize(g_timing.ev[2]));
+    CUDA_TRY(cudaEventSynchronize(g_timing.ev[3]));
     CUDA_TRY(cudaEventElapsedTime(&ms[0], g_timing.ev[0], g_timing.ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&ms[1], g_timing.ev[1], g_timing.ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms[2], g_timing.ev[2], g_timing.ev[3]));
     return 0;
 }
 

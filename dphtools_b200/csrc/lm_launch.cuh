@@ -638,7 +638,7 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
         if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
         rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream);
         if (rc) return rc;
-        if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));
+        if (a.ev) { CUDA_TRY(cudaEventRecord(a.ev[2], stream)); CUDA_TRY(cudaEventRecord(a.ev[3], stream)); }
         return 0;
     }
     DeviceCtx::Side& sd = ctx->sides[ctx->next_side++ % 4];  // the caller holds ctx->fork_mu
@@ -677,12 +677,13 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     const bool early = !a.ev && !getenv("DPHLM_NO_EARLY_START");
     rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream, 2 * kPollerCtas, 0, early);
     if (rc) return rc;
+    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));  // end of the lm() main kernel itself
     rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, bw, 1, smem_w, ctx, sd.stream_b, 0, kPollerCtas);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(sd.join_b, sd.stream_b));
     CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_a, 0));
     CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_b, 0));
-    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));
+    if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[3], stream));  // the pollers have finished the stragglers
     return 0;
 }
 

@@ -125,9 +125,11 @@ int dphlm_extract_rois(const dphlm_extract_desc* d, void* stream);
 void* dphlm_host_alloc(size_t bytes);
 void dphlm_host_free(void* p);
 
-/* Durations (ms, CUDA events on the launch stream) of the pre-fit kernel and of the lm() kernel of this
- * thread's last dphlm_fit_batch call that had DPHLM_FLAG_TIMING set; waits for that call to finish. */
-int dphlm_last_kernel_ms(float ms[2]);
+/* Durations (ms, CUDA events on the launch stream) of this thread's last dphlm_fit_batch call that had DPHLM_FLAG_TIMING set:
+ * ms[0] the pre-fit main kernel, ms[1] the lm() main kernel, ms[2] from the end of the lm() main kernel until the poller
+ * kernels have finished the last straggler (the pollers run concurrently with the main kernels; a pre-fit that needs
+ * hundreds of evaluations ends here).  Waits for that call to finish. */
+int dphlm_last_kernel_ms(float ms[3]);
 
 int dphlm_device_count(void);
 int dphlm_version(void);

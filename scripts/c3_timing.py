@@ -8,6 +8,6 @@ data = torch.cat([torch.from_numpy(p["data"]) for p in parts]).cuda(); p0 = torc
 dph.curve_fit_batch(models.gauss2d, data[:1000], p0[:1000], "mle"); torch.cuda.synchronize()
 for rep in range(2):
     r = dph.curve_fit_batch(models.gauss2d, data, p0, "mle", timing=True, return_counts=True)
-    a, b = _lib.last_kernel_ms()
+    a, b, _tail = _lib.last_kernel_ms()
     c = r.counts.cpu().numpy()
     print("n=%d: prefit(main) %.2f ms, rest (lm main + pollers) %.2f ms -> %.3e fits/s | parked-ish: A>16: %d  B>=24: %d  A>=300: %d" % (n, a, b, n / (a + b) * 1e3, (c[:, 0] > 16).sum(), (r.nfev.cpu().numpy() >= 24).sum(), (c[:, 0] >= 300).sum()))
