@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libdphlm.so")
-SOURCES = ["lm_kernels.cu", "roi_extract.cu", "lm_inst_gauss2d.cu", "lm_inst_ellip.cu", "lm_inst_gint.cu", "lm_inst_gintf.cu", "lm_inst_mexp1.cu", "lm_inst_mexp2.cu", "lm_inst_mexp3.cu", "lm_inst_mexp_irf.cu"]
+SOURCES = ["lm_kernels.cu", "roi_extract.cu", "lm_inst_gauss2d.cu", "lm_inst_gauss2df.cu", "lm_inst_ellip.cu", "lm_inst_gint.cu", "lm_inst_gintf.cu", "lm_inst_mexp1.cu", "lm_inst_mexp2.cu", "lm_inst_mexp3.cu", "lm_inst_mexp_irf.cu"]
 DEPS = ["lm_core.cuh", "lm_launch.cuh", os.path.join("..", "..", "include", "dphlm.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",

@@ -306,6 +306,60 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     }
 };
 
+// The sampled symmetric Gaussian with the width held at consts[0]: amp, x0, y0, offset (the
+// fixed-width variant for the pixel-centre model; the erf form is Gauss2DIntegratedFixed).  Same step algebra as Gauss2D
+// with d_sigma = 0.
+struct Gauss2DFixed {
+    static constexpr int P = 4, NE = 1, kMinCtas = 3;
+    struct Par { float amp, x0, y0, off, sig = 1.0f, s2 = 1.0f, nh = -0.5f * 1.4426950408889634f, as2; };
+    struct Step { float d0, d1, d2, d3, nh1, ndd, c2, k0; };
+    template <class T> struct Geo { T dx, dy, r2; };
+    template <class T> struct Diff { T dot, dr2; };
+    static constexpr int kTable = 0;
+    static constexpr bool kStoreE = true;
+    DPH_HD static int table_floats(int, int) { return 0; }
+    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
+    DPH_HD static void set_consts(Par& q, const float* consts) {
+        if (!consts) return;
+        q.sig = consts[0];
+        const float is = f_rcp(q.sig);
+        q.s2 = is * is;
+        q.nh = -0.5f * kLog2e * q.s2;
+    }
+    DPH_HD static void prepare(const float* p, Par& q) {
+        q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.off = p[3];
+        q.as2 = q.amp * q.s2;
+    }
+    template <class T> DPH_HD static void geometry(const Par& q, T cx, T cy, Geo<T>& g) {
+        g.dx = cx - T(q.x0); g.dy = cy - T(q.y0); g.r2 = f_fma(g.dx, g.dx, g.dy * g.dy);
+    }
+    template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) { e[0] = v_ex2(g.r2 * T(q.nh)); }
+    template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
+    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
+        T t = e[0] * T(q.as2);
+        J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = T(1.0f);
+    }
+    DPH_HD static void prepare_step(const Par& a, const Par&, const float* d, Step& s) {
+        s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3];
+        s.nh1 = -0.5f * a.s2;
+        s.ndd = -f_fma(d[1], d[1], d[2] * d[2]);
+        s.c2 = a.amp * a.s2;
+        s.k0 = f_fma(-s.c2, s.ndd, d[0]);  // d0 + c2 (d1^2 + d2^2)
+    }
+    template <class T> DPH_HD static void diff(const Par&, const Step& s, const Geo<T>& g1, Diff<T>& df) {
+        df.dot = f_fma(g1.dx, T(s.d1), g1.dy * T(s.d2));
+        df.dr2 = f_fma(T(-2.0f), df.dot, T(s.ndd));  // r2_new - r2_old
+    }
+    template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
+        T darg = df.dr2 * T(s.nh1);
+        T de = v_sel_small(darg, kSmallArg, ea[0] * expm1_small(darg), eb[0] - ea[0]);
+        return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d3)));
+    }
+    template <class T> DPH_HD static T jdx(const Par&, const Step& s, const Diff<T>& df, const T* ea) {
+        return f_fma(ea[0], f_fma(T(s.c2), df.dot, T(s.k0)), T(s.d3));
+    }
+};
+
 struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     static constexpr int P = 7, NE = 1, kMinCtas = 2;
     struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy; };

@@ -45,7 +45,7 @@ int get_ctx(int dev, DeviceCtx** out) {
 // number of floats `consts` holds for a model (host path: `consts` is a host pointer)
 constexpr int kMaxConsts = 3 + 32;
 int model_consts(int model, const float* consts) {
-    if (model == DPHLM_GAUSS2D_INTEGRATED_FIXED) return 1;
+    if (model == DPHLM_GAUSS2D_INTEGRATED_FIXED || model == DPHLM_GAUSS2D_FIXED) return 1;
     if (model == DPHLM_MULTI_EXP_IRF && consts) {
         const int w = (int)consts[0];
         return 3 + (w < 1 ? 1 : w > 32 ? 32 : w);
@@ -81,6 +81,10 @@ int validate_shape(const dphlm_desc* d) {
             if (d->n_param != 4) return fail("gauss2d_integrated_fixed takes 4 parameters");
             if (d->dim0 > 32 || d->dim1 > 32) return fail("gauss2d_integrated_fixed: ROI sides up to 32 pixels");
             if (!d->consts && d->n_fits > 0) return fail("gauss2d_integrated_fixed needs consts[0] = sigma");
+            break;
+        case DPHLM_GAUSS2D_FIXED:
+            if (d->n_param != 4) return fail("gauss2d_fixed takes 4 parameters");
+            if (!d->consts && d->n_fits > 0) return fail("gauss2d_fixed needs consts[0] = sigma");
             break;
         case DPHLM_MULTI_EXP_IRF:
             if (d->n_param < 2 || d->n_param > 5) return fail("multi_exp_irf supports 2..5 parameters (1-2 exponentials, optional offset)");
@@ -148,6 +152,7 @@ int launch_model(const dphlm_desc* d, int G, const KArgs& a, const ParkLists& pl
         case DPHLM_GAUSS2D_INTEGRATED: return launch_gauss2d_integrated(G, mle, a, pl, ctx, s);
         case DPHLM_GAUSS2D_INTEGRATED_FIXED: return launch_gauss2d_integrated_fixed(G, mle, a, pl, ctx, s);
         case DPHLM_MULTI_EXP_IRF: return launch_multi_exp_irf(d->n_param, G, mle, a, pl, ctx, s);
+        case DPHLM_GAUSS2D_FIXED: return launch_gauss2d_fixed(G, mle, a, pl, ctx, s);
         case DPHLM_MULTI_EXP:
             switch (d->n_param / 2) {
                 case 1: return launch_multi_exp1(d->n_param & 1, G, mle, a, pl, ctx, s);
@@ -361,6 +366,7 @@ int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int ki
         case DPHLM_GAUSS2D_INTEGRATED: return launch_cov_gauss2d_integrated(a, s);
         case DPHLM_GAUSS2D_INTEGRATED_FIXED: return launch_cov_gauss2d_integrated_fixed(a, s);
         case DPHLM_MULTI_EXP_IRF: return launch_cov_multi_exp_irf(d->n_param, a, s);
+        case DPHLM_GAUSS2D_FIXED: return launch_cov_gauss2d_fixed(a, s);
         case DPHLM_MULTI_EXP: return launch_cov_multi_exp(d->n_param, a, s);
     }
     return fail("unknown model id");

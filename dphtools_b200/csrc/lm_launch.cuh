@@ -707,6 +707,8 @@ int launch_cov_gauss2d(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_elliptical(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_integrated(const CovArgs& a, cudaStream_t s);
 int launch_cov_gauss2d_integrated_fixed(const CovArgs& a, cudaStream_t s);
+int launch_gauss2d_fixed(int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
+int launch_cov_gauss2d_fixed(const CovArgs& a, cudaStream_t s);
 int launch_multi_exp_irf(int n_param, int G, bool mle, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s);
 int launch_cov_multi_exp_irf(int n_param, const CovArgs& a, cudaStream_t s);
 int launch_cov_multi_exp(int n_param, const CovArgs& a, cudaStream_t s);

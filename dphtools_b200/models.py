@@ -15,6 +15,7 @@ Conventions:
 * ``gauss2d``:  ``amp * exp(-((x-x0)^2 + (y-y0)^2) / (2 sigma^2)) + offset``
 * ``gauss2d_integrated``: ``amp * Ex(x) * Ey(y) + offset`` with ``Ex`` the integral of a unit-area Gaussian over the pixel
   (erf model of a pixelated camera); ``amp`` is the photon count of the spot.
+* ``gauss2d_fixed(sigma)``: factory for ``gauss2d`` with the width held at ``sigma`` (4 parameters).
 * ``gauss2d_integrated_fixed(sigma)``: factory for the 4-parameter ``(amp, x0, y0, offset)`` version with the width held
   at ``sigma`` (the model of ``notebooks/MLE_LevMarq_4Param_2013_11_12.m`` upstream, whose PSF width is a call argument).
 * ``multi_exp_convolved(irf, dt, m0)``: factory for ``multi_exp`` convolved with an instrument response function sampled on
@@ -32,6 +33,7 @@ MODEL_MULTI_EXP = 2
 MODEL_GAUSS2D_INTEGRATED = 3
 MODEL_GAUSS2D_INTEGRATED_FIXED = 4
 MODEL_MULTI_EXP_IRF = 5
+MODEL_GAUSS2D_FIXED = 6
 ONE_D = (MODEL_MULTI_EXP, MODEL_MULTI_EXP_IRF)  # models of a 1-D histogram: need the shared x axis
 IRF_MAX_TAPS = 32
 
@@ -114,6 +116,24 @@ def gauss2d_integrated_jac(xy, amp, x0, y0, sigma, offset):
     ex, dex, sex = _pixel_integral(xy[0] - x0, sigma)
     ey, dey, sey = _pixel_integral(xy[1] - y0, sigma)
     return np.stack([ex * ey, amp * dex * ey, amp * ex * dey, amp * (sex * ey + ex * sey), np.ones_like(ex)], axis=1)
+
+
+def gauss2d_fixed(sigma):
+    """:func:`gauss2d` with the width held at ``sigma``: returns the model ``f(xy, amp, x0, y0, offset)`` (with ``f.jac``);
+    ``f.consts = (sigma,)`` travels to the kernels as ``dphlm_desc.consts``."""
+    sigma = float(sigma)
+    if not sigma > 0:
+        raise ValueError("sigma must be positive")
+
+    def model(xy, amp, x0, y0, offset):
+        return gauss2d(xy, amp, x0, y0, sigma, offset)
+
+    def jac(xy, amp, x0, y0, offset):
+        return gauss2d_jac(xy, amp, x0, y0, sigma, offset)[:, [0, 1, 2, 4]]
+
+    _tag(model, jac, MODEL_GAUSS2D_FIXED, 4, "gauss2d_fixed")
+    model.consts = (sigma,)
+    return model
 
 
 def gauss2d_integrated_fixed(sigma):
@@ -224,6 +244,8 @@ def resolve(name, consts=None):
     """Model by name; the factories are called with the constants they stored in ``f.consts``."""
     if name == "gauss2d_integrated_fixed":
         return gauss2d_integrated_fixed(consts[0])
+    if name == "gauss2d_fixed":
+        return gauss2d_fixed(consts[0])
     if name == "multi_exp_convolved":
         w = int(consts[0])
         return multi_exp_convolved(consts[3:3 + w], consts[2], int(consts[1]))

@@ -80,6 +80,14 @@ def gauss2d_integrated_fixed_rois(n, size=11, seed=0, sigma=1.3):
     return dict(data=w["data"], p0=np.ascontiguousarray(w["p0"][:, keep]), truth=w["truth"][:, keep], xaxis=None, consts=(sigma,))
 
 
+def gauss2d_fixed_rois(n, size=11, seed=0, sigma=1.3):
+    """Sampled Gaussian spots of one known width, fitted with the width held there: ``p0 = (amp, x0, y0, offset)``."""
+    sigma = float(np.float32(sigma))
+    w = gauss2d_rois(n, size, seed, sigma=(sigma, sigma))
+    keep = [0, 1, 2, 4]
+    return dict(data=w["data"], p0=np.ascontiguousarray(w["p0"][:, keep]), truth=w["truth"][:, keep], xaxis=None, consts=(sigma,))
+
+
 def gauss2d_elliptical_p0(data):
     n, h, w = data.shape
     flat = data.reshape(n, -1)
@@ -203,4 +211,5 @@ WORKLOADS = {
     "c6_gauss2d_int_11": lambda n, seed=0: gauss2d_integrated_rois(n, 11, seed),
     "c7_gauss2d_intf_11": lambda n, seed=0: gauss2d_integrated_fixed_rois(n, 11, seed),
     "c8_multiexp_irf_256": lambda n, seed=0: multi_exp_irf_hists(n, 256, seed),
+    "c9_gauss2d_fixed_11": lambda n, seed=0: gauss2d_fixed_rois(n, 11, seed),
 }

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define DPHLM_VERSION 101
+#define DPHLM_VERSION 102
 
 /* model ids: callables a caller would pass as `f` to curve_fit (dphtools/utils/lm.py:510-512).
  * MULTI_EXP is the reference's own model (dphtools/utils/fitfuncs.py:20-52); the Gaussians are new:
@@ -26,12 +26,13 @@ extern "C" {
  * the pixel centres; GAUSS2D_INTEGRATED (photons, x0, y0, sigma, offset) integrated over each pixel (erf model);
  * GAUSS2D_INTEGRATED_FIXED (photons, x0, y0, offset) the same with the width held at consts[0] (the 4-parameter model of
  * notebooks/MLE_LevMarq_4Param_2013_11_12.m:44-54, where the PSF width is an argument of the call);
+ * GAUSS2D_FIXED (amp, x0, y0, offset): GAUSS2D with the width held at consts[0];
  * MULTI_EXP_IRF: MULTI_EXP (1-2 exponentials, optional offset) convolved with an instrument response function given on the
  * histogram's own uniform grid: f_j = offset + sum_i a_i sum_q irf[q] exp(-k_i (j - m0 - q) dt) over 0 <= q < W, q <= j - m0;
  * consts = [W (<= 32), m0, dt, irf[0..W-1]].  Built for group_lanes 0, 16, 32. */
 enum dphlm_model {
     DPHLM_GAUSS2D = 0, DPHLM_GAUSS2D_ELLIPTICAL = 1, DPHLM_MULTI_EXP = 2, DPHLM_GAUSS2D_INTEGRATED = 3,
-    DPHLM_GAUSS2D_INTEGRATED_FIXED = 4, DPHLM_MULTI_EXP_IRF = 5
+    DPHLM_GAUSS2D_INTEGRATED_FIXED = 4, DPHLM_MULTI_EXP_IRF = 5, DPHLM_GAUSS2D_FIXED = 6
 };
 
 /* `method` of curve_fit / lm (dphtools/utils/lm.py:235, 519, 621-626) */
@@ -48,7 +49,7 @@ enum dphlm_method { DPHLM_LS = 0, DPHLM_MLE = 1 };
 typedef struct dphlm_desc {
     int32_t model;       /* enum dphlm_model */
     int32_t method;      /* enum dphlm_method */
-    int32_t n_param;     /* 5 (GAUSS2D, GAUSS2D_INTEGRATED), 4 (.._FIXED), 7 (ELLIPTICAL), 2..7 (MULTI_EXP: 2 per exponential, +1 = offset) */
+    int32_t n_param;     /* 5 (GAUSS2D, GAUSS2D_INTEGRATED), 4 (their _FIXED forms), 7 (ELLIPTICAL), 2..7 (MULTI_EXP: 2 per exponential, +1 = offset) */
     int32_t dim0, dim1;  /* ROI height, width; (n_bins, 1) for 1-D models */
     int32_t group_lanes; /* lanes of a warp that own one fit: 0 = automatic, else 2, 4, 8, 16 or 32 */
     int64_t n_fits;
@@ -66,7 +67,7 @@ typedef struct dphlm_desc {
     float ftol, xtol, gtol, factor; /* lm()/leastsq keywords, forwarded to both stages (lm.py:643, 668) */
     int32_t maxfev;      /* <= 0: 100 * (n_param + 1)                                   (lm.py:306-307) */
     int32_t flags;       /* DPHLM_FLAG_* */
-    const float* consts; /* constants of the model, shared by all fits: GAUSS2D_INTEGRATED_FIXED: [1] sigma;
+    const float* consts; /* constants of the model, shared by all fits: GAUSS2D_FIXED, GAUSS2D_INTEGRATED_FIXED: [1] sigma;
                             MULTI_EXP_IRF: [3 + W] = W, m0, dt, irf[0..W-1]; else NULL */
 } dphlm_desc;
 

@@ -3,7 +3,7 @@
 import numpy as np
 
 # parameters on which the north-star tolerance (relative 1e-4) is stated: amplitude, centre, width
-KEY_PARAMS = {"gauss2d": [0, 1, 2, 3], "gauss2d_integrated": [0, 1, 2, 3], "gauss2d_integrated_fixed": [0, 1, 2], "gauss2d_elliptical": [0, 1, 2, 3, 4], "multi_exp": [0, 1, 2, 3],
+KEY_PARAMS = {"gauss2d": [0, 1, 2, 3], "gauss2d_integrated": [0, 1, 2, 3], "gauss2d_integrated_fixed": [0, 1, 2], "gauss2d_fixed": [0, 1, 2], "gauss2d_elliptical": [0, 1, 2, 3, 4], "multi_exp": [0, 1, 2, 3],
               "multi_exp_convolved": [0, 1, 2, 3]}
 
 

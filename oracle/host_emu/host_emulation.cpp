@@ -160,6 +160,7 @@ extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, l
     if (model == 1 && n_param == 7) RUN(Gauss2DElliptical);
     if (model == 3 && n_param == 5) RUN(Gauss2DIntegrated);
     if (model == 4 && n_param == 4 && consts) RUN(Gauss2DIntegratedFixed);
+    if (model == 6 && n_param == 4 && consts) RUN(Gauss2DFixed);
     if (model == 5 && n_param == 2 && consts) RUN(MultiExpIrf<1, false>);
     if (model == 5 && n_param == 3 && consts) RUN(MultiExpIrf<1, true>);
     if (model == 5 && n_param == 4 && consts) RUN(MultiExpIrf<2, false>);

@@ -45,9 +45,11 @@ SETS = {
     "c6_ls": ("c6_gauss2d_int_11", 1000, 16, "ls"),
     "c7_ls": ("c7_gauss2d_intf_11", 1000, 17, "ls"),
     "c8_ls": ("c8_multiexp_irf_256", 500, 18, "ls"),
+    "c9_mle": ("c9_gauss2d_fixed_11", 1000, 9, "mle"),
 }
 MODEL_OF = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp, "c6": models.gauss2d_integrated,
-            "c7": models.gauss2d_integrated_fixed(1.3), "c8": models.multi_exp_convolved([1.0], 1.0)}
+            "c7": models.gauss2d_integrated_fixed(1.3), "c8": models.multi_exp_convolved([1.0], 1.0),
+            "c9": models.gauss2d_fixed(1.3)}
 
 _G = {}
 

@@ -15,7 +15,7 @@ import dphtools_b200 as dph  # noqa: E402
 from dphtools_b200 import models, synth  # noqa: E402
 
 MODEL = {"c1": models.gauss2d, "c2": models.gauss2d, "c3": models.gauss2d, "c4": models.gauss2d_elliptical, "c5": models.multi_exp,
-         "c6": models.gauss2d_integrated, "c7": models.gauss2d_integrated_fixed(1.3)}
+         "c6": models.gauss2d_integrated, "c7": models.gauss2d_integrated_fixed(1.3), "c9": models.gauss2d_fixed(1.3)}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("workload")

@@ -16,7 +16,7 @@ torch = pytest.importorskip("torch")
 CASES = [
     ("c1_mle", 0.99, 1.0), ("c2_mle", 0.995, 1.0), ("c2_ls", 0.99, 1.0), ("c3_mle", 0.995, 0.999),
     ("c4_mle", 0.995, 1.0), ("c4_ls", 0.995, 1.0), ("c5_mle", 0.995, 1.0), ("c5_ls", 0.995, 1.0), ("c6_mle", 0.99, 1.0),
-    ("c8_mle", 0.99, 1.0), ("c6_ls", 0.99, 1.0), ("c7_ls", 0.99, 1.0), ("c8_ls", 0.99, 1.0),
+    ("c8_mle", 0.99, 1.0), ("c6_ls", 0.99, 1.0), ("c7_ls", 0.99, 1.0), ("c8_ls", 0.99, 1.0), ("c9_mle", 0.97, 1.0),
     ("c7_mle", 0.97, 1.0),  # fixed width: quadratic convergence ends with ftol and xtol both borderline -> more 1<->2 swaps
 ]
 

@@ -23,14 +23,14 @@ def _spots(model, h, w, n, seed, sigma_fixed=None):
     photons = rng.uniform(300, 4000, n)
     data = np.empty((n, h, w), np.float32)
     for i in range(n):
-        if model.model_name == "gauss2d":
+        if model.model_name in ("gauss2d", "gauss2d_fixed"):
             mu = models.gauss2d(xy, photons[i] / (2 * np.pi * sig[i] ** 2), x0[i], y0[i], sig[i], bg[i])
         else:
             mu = models.gauss2d_integrated(xy, photons[i], x0[i], y0[i], sig[i], bg[i])
         data[i] = rng.poisson(mu).reshape(h, w)
     flat = data.reshape(n, -1)
     mn, mx = flat.min(1), flat.max(1)
-    amp = mx - mn if model.model_name == "gauss2d" else np.maximum((flat - mn[:, None]).sum(1), 1.0)
+    amp = mx - mn if model.model_name in ("gauss2d", "gauss2d_fixed") else np.maximum((flat - mn[:, None]).sum(1), 1.0)
     cols = [amp, np.full(n, (w - 1) / 2), np.full(n, (h - 1) / 2)]
     if model.n_param == 5:
         cols.append(np.full(n, 1.2))
@@ -51,6 +51,7 @@ CASES = [
     (lambda: models.gauss2d_integrated, 7, 7, 1000, 2),
     (lambda: models.gauss2d_integrated_fixed(1.15), 8, 11, 300, 4),
     (lambda: models.gauss2d_integrated_fixed(1.15), 11, 8, 14300, 0),   # a little more than one wave of 4-lane groups
+    (lambda: models.gauss2d_fixed(1.15), 10, 7, 300, 0),
     (lambda: models.gauss2d, 25, 25, 200, 0),
     (lambda: models.gauss2d_integrated, 31, 29, 100, 0),
 ]

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.dphlm_version() == 101
+    assert lib.dphlm_version() == 102
 
 
 def test_desc_layout_and_defaults():

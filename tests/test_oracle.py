@@ -6,7 +6,7 @@ import pytest
 from dphtools_b200 import models
 from oracle import lm_oracle
 
-SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle", "c7_mle", "c8_mle", "c6_ls", "c7_ls", "c8_ls"]
+SETS = ["c1_mle", "c2_mle", "c2_ls", "c3_mle", "c4_mle", "c4_ls", "c5_mle", "c5_ls", "c6_mle", "c7_mle", "c8_mle", "c6_ls", "c7_ls", "c8_ls", "c9_mle"]
 
 
 def _xdata(g):
@@ -52,6 +52,7 @@ def test_oracle_curve_fit_surface(golden):
     (models.gauss2d_elliptical, (50.0, 7.3, 6.6, 1.4, 2.1, 0.3, 3.0)),
     (models.gauss2d_integrated, (1500.0, 7.3, 6.6, 1.4, 3.0)),
     (models.gauss2d_integrated_fixed(1.25), (1500.0, 7.3, 6.6, 3.0)),
+    (models.gauss2d_fixed(1.25), (50.0, 7.3, 6.6, 3.0)),
     (models.multi_exp, (900.0, 2.2, 300.0, 0.4, 4.0)),
     (models.multi_exp_convolved([0.1, 0.2, 0.4, 0.2, 0.1], 0.05, 6), (900.0, 2.2, 300.0, 0.4, 4.0)),
     (models.multi_exp_convolved([0.1, 0.2, 0.4, 0.2, 0.1], 0.05, 6), (900.0, 2.2)),
