@@ -541,7 +541,7 @@ struct Gauss2DIntegratedT {
         g.exa = cb.a; g.ux = cb.b; g.eya = rb.a; g.uy = rb.b;
     }
     template <class T> DPH_HD static void expo(const Par&, const Geo<T>& g, T* e) { e[0] = g.ex * g.ey; }
-    template <class T> DPH_HD static void expo_old(const Geo<T>& g, T* e) { e[0] = g.exa * g.eya; }  // at the accepted point
+    template <class T> DPH_HD static void expo_old(const Par&, const Geo<T>& g, T* e) { e[0] = g.exa * g.eya; }  // at the accepted point
     template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
     template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
         J[0] = e[0];
@@ -639,21 +639,25 @@ struct MultiExp {
 //   C = e S[w],  D = -dC/dk = u C - e T[w],   w = min(j - m0, W-1),
 //   S[w] = sum_{q<=w} irf[q] exp(k q dt),  T[w] = sum_{q<=w} irf[q] q dt exp(k q dt)
 // so one exponential per bin and two prefix-sum tables per exponential and trial point (fill_tables: a shuffle scan over
-// the lanes of the group, in the group's shared memory).  C and D are the per-bin values stored between trips (NE = 2 NEXP),
-// which makes J(x) d at the accepted point free, and f(x+d) - f(x) uses dC = -dk (D_a + D_b)/2 (trapezoid rule on dC/dk,
+// the lanes of the group, in the group's shared memory; the tables of the accepted point are kept, accepting a step flips the
+// two buffers).  C and D of both points are rebuilt per bin from the tables, so the model keeps no per-bin state, J(x) d at the
+// accepted point comes from its C and D, and f(x+d) - f(x) uses dC = -dk (D_a + D_b)/2 (trapezoid rule on dC/dk,
 // relative error (dk u)^2 / 12) for small dk u and the direct difference otherwise.
 constexpr int kIrfTaps = 32;
 template <int NEXP, bool OFFSET>
 struct MultiExpIrf {
-    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = 2 * NEXP, kMinCtas = 2;
-    static constexpr int kTable = 2 * NEXP * kIrfTaps;
-    static constexpr bool kStoreE = true;
+    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = 2 * NEXP, kMinCtas = 3;
+    static constexpr int kHalf = 2 * NEXP * kIrfTaps;  // one buffer: S and T per exponential
+    static constexpr int kTable = 2 * kHalf;           // accepted point and trial point; accepting a step flips which is which
+    static constexpr bool kStoreE = false;             // C and D of the accepted point are rebuilt from its tables
     DPH_HD static int table_floats(int, int) { return kTable; }
     static constexpr float kTrapz = 0.009f;  // |dk u| below which the trapezoid rule beats the direct difference in fp32
     struct Par {
         float a[NEXP], k[NEXP], off;
         const float* consts = nullptr;  // [W, m0, dt, irf...]
         const float* tbl = nullptr;     // [NEXP][2][kIrfTaps] of this trial point
+        const float* tbla = nullptr;    // the same of the accepted point
+        float ka[NEXP];                 // rates of the accepted point
         float m0 = 0.0f, dt = 1.0f, wmax = 0.0f;
     };
     struct Step { float da[NEXP], dk[NEXP], doff; };
@@ -671,11 +675,17 @@ struct MultiExpIrf {
         q.off = OFFSET ? p[2 * NEXP] : 0.0f;
     }
     // prefix sums S, T over the IRF taps for every exponential of the point q, by the lanes of the group
-    template <class L> DPH_HD static void fill_tables(const L& ln, const Par&, Par& q, Step&, float* tbl, int, int, int) {
-        q.tbl = tbl;
+    template <class L> DPH_HD static void fill_tables(const L& ln, const Par& q0, Par& q, Step&, float* tbl, int, int, int phase) {
+        const int cur = phase & 1;
+        const bool init = phase & 2;
+        float* trial = tbl + (cur ? 0 : kHalf);
+        float* acc = tbl + (cur ? kHalf : 0);
+        q.tbl = trial; q.tbla = acc;
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) q.ka[i] = q0.k[i];
         if (!q.consts) return;  // idle group
         constexpr int G = L::kLanes;
-        ln.sync();  // the previous pass has finished reading the table
+        ln.sync();  // the previous pass has finished reading the tables
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) {
             float carry_s = 0.0f, carry_t = 0.0f;
@@ -691,8 +701,12 @@ struct MultiExpIrf {
                     if (ln.lane >= o) { s += us; t += ut; }
                 }
                 s += carry_s; t += carry_t;
-                tbl[(2 * i) * kIrfTaps + w] = s;
-                tbl[(2 * i + 1) * kIrfTaps + w] = t;
+                trial[(2 * i) * kIrfTaps + w] = s;
+                trial[(2 * i + 1) * kIrfTaps + w] = t;
+                if (init) {  // first pass of a fit: the accepted point is the trial point
+                    acc[(2 * i) * kIrfTaps + w] = s;
+                    acc[(2 * i + 1) * kIrfTaps + w] = t;
+                }
                 carry_s = ln.bcast(s, G - 1);
                 carry_t = ln.bcast(t, G - 1);
             }
@@ -706,15 +720,17 @@ struct MultiExpIrf {
         g.in = v_nonneg01(jj);
         g.w = v_clamp(jj, 0.0f, q.wmax);
     }
-    template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) {
+    template <class T> DPH_HD static void conv(const float* tbl, const float* k, const Geo<T>& g, T* e) {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) {
-            const T ex = v_ex2(g.u * T(-kLog2e * q.k[i])) * g.in;
-            const T c = ex * v_gather(q.tbl + (2 * i) * kIrfTaps, g.w);
+            const T ex = v_ex2(g.u * T(-kLog2e * k[i])) * g.in;
+            const T c = ex * v_gather(tbl + (2 * i) * kIrfTaps, g.w);
             e[2 * i] = c;
-            e[2 * i + 1] = g.u * c - ex * v_gather(q.tbl + (2 * i + 1) * kIrfTaps, g.w);
+            e[2 * i + 1] = g.u * c - ex * v_gather(tbl + (2 * i + 1) * kIrfTaps, g.w);
         }
     }
+    template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) { conv(q.tbl, q.k, g, e); }
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, T* e) { conv(q.tbla, q.ka, g, e); }  // accepted point
     template <class T> DPH_HD static T value(const Par& q, const T* e) {
         T f = T(q.off);
 #pragma unroll
@@ -896,7 +912,7 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
 #pragma unroll
         for (int j = 0; j < NE; ++j) e0[j] = v_pick(init, e1[j], e0in[j]);
     } else {
-        Mo::expo_old(g1, e0);  // on the first pass the tables of the accepted point equal the trial ones
+        Mo::expo_old(q1, g1, e0);  // on the first pass the tables of the accepted point equal the trial ones
     }
     Mo::diff(q0, st, g1, df);
     const T f0 = Mo::value(q0, e0);
@@ -1018,7 +1034,7 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
                     e1b[j * stride + i] = e1[j];
                 }
             } else {
-                Mo::expo_old(g1, e0);
+                Mo::expo_old(q1, g1, e0);
             }
             const float y = px.y[i];
             Mo::diff(q0, st, g1, df);
