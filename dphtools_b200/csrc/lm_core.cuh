@@ -33,6 +33,9 @@
 #define DPH_HD inline
 #endif
 
+#ifndef DPH_GAUSS2D_STORE
+#define DPH_GAUSS2D_STORE false
+#endif
 #ifndef DPH_PAIR_UNROLL
 #define DPH_PAIR_UNROLL 1  // unroll factor of the pixel-pair loop (registers vs instruction-level parallelism)
 #endif
@@ -255,14 +258,20 @@ DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
 
 struct Gauss2D {  // amp, x0, y0, sigma, offset
     static constexpr int P = 5, NE = 1, kMinCtas = 3;
-    struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3; };
+    struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3, ad1, ad2, anh; };  // a*: step from / exponent scale of the accepted point
     struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
     template <class T> struct Geo { T dx, dy, r2; };
     template <class T> struct Diff { T dot, dr2, r20; };
     static constexpr int kTable = 0;
-    static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
+    static constexpr bool kStoreE = DPH_GAUSS2D_STORE;  // false: the accepted point's exponential is recomputed, nothing per pixel is kept
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
+    template <class L> DPH_HD static void fill_tables(const L&, const Par& q0, Par& q1, Step&, float*, int, int, int) {
+        q1.ad1 = q1.x0 - q0.x0; q1.ad2 = q1.y0 - q0.y0; q1.anh = q0.nh;
+    }
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, T* e) {
+        const T dxa = g.dx + T(q.ad1), dya = g.dy + T(q.ad2);
+        e[0] = v_ex2(f_fma(dxa, dxa, dya * dya) * T(q.anh));
+    }
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
