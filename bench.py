@@ -345,7 +345,7 @@ def main():
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
                 # dram__bytes_read+write of the lm() main launch from the ncu --set full capture of this workload
-                # (profiles/r1_ncu_full_final_gauss2d_11x11_G4.txt); algorithmic: 484 B/fit read again + 32 B/fit written
+                # (profiles/r1_ncu_full_v4_gauss2d_11x11_G4.txt); algorithmic: 484 B/fit read again + 32 B/fit written
                 "traffic": 51.2e6 * n / 1e5, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; the main launch, events around it)",
                 "kernel_ms": k_main * 1e3, "share_of_step": k_main / k_s,
                 "straggler_tail_ms": k_tail * 1e3,  # after the lm() kernel: the pollers finishing the longest straggler (mean over the input sets)
