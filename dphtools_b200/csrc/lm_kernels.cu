@@ -53,11 +53,12 @@ int model_consts(int model, const float* consts) {
     return 0;
 }
 
-int auto_group(int M, int model) {
-    // measured on B200 (profiles/): 7x7 -> 2 lanes, 11x11 -> 4 (2 is 5 % faster from 4e5 fits per call on and equal at 1e5),
-    // 15x15 -> 4 for the sampled Gaussian, which keeps no per-pixel state in shared memory, 8 otherwise; 256 bins -> 16
+int auto_group(int M, int model, long long n_fits) {
+    // measured on B200 (profiles/): 7x7 -> 2 lanes; 11x11 -> 4, and 2 for the sampled Gaussian from 3e5 fits per call on (5 %
+    // faster there: the per-trip scalar work is shared by 16 fits; equal at 1e5, where the longer per-fit latency shows in the
+    // tails); 15x15 -> 4 for the sampled Gaussian, which keeps no per-pixel state in shared memory, 8 otherwise; 256 bins -> 16
     if (M <= 64) return 2;
-    if (M <= 128) return 4;
+    if (M <= 128) return model == DPHLM_GAUSS2D && n_fits >= 300000 ? 2 : 4;
     if (M <= 240) return model == DPHLM_GAUSS2D ? 4 : 8;
     return 16;
 }
@@ -179,7 +180,7 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
         a.ev = g_timing.ev;
         g_timing.valid = true;
     }
-    const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w, d->model);
+    const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w, d->model, d->n_fits);
     // workspace: pre-fit exit codes, and the pre-fit parameters when the caller does not want them
     const size_t b_ier = ((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255);
     const size_t b_park = park_bytes(d->n_fits);
