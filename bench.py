@@ -7,9 +7,10 @@
 One "step" = one pass of the hot path over one batch of 1e5 synthetic Poisson-noised spots per GPU (weak
 scaling: each rank fits its own shard, no data-path collective).  `value` is whole-job
 fits/s with the inputs resident in HBM; `e2e` is the same through the public API with pinned HOST buffers
-(H2D + kernel + D2H inside the timed region).  The reference arm times the float64 oracle port of
-dphtools.utils.lm.curve_fit (scipy MINPACK pre-fit + lm(); the Python reference itself cannot travel to the
-GPU box) with one process per host core on a bounded sample of the same workload.
+(H2D + kernel + D2H inside the timed region).  The reference arm times the reference's own
+dphtools.utils.lm.curve_fit (scipy MINPACK pre-fit + lm()) from oracle/_ref (placed there by oracle/build_ref.py at
+build time; the float64 port oracle/lm_oracle.py only if that is absent) with one process per host core on a bounded
+sample of the same workload.
 """
 
 import argparse
@@ -38,14 +39,36 @@ def _cpu_fit_chunk(args):
     data, p0 = args
     os.environ["OMP_NUM_THREADS"] = "1"
     from dphtools_b200 import models
-    from oracle import lm_oracle
+    from oracle import build_ref, lm_oracle
 
-    out = lm_oracle.fit_batch(models.gauss2d, data, p0, "mle", models.roi_grid(ROI, ROI))
-    return out["popt"], out["info"], out["nfev"]
+    xy = models.roi_grid(ROI, ROI)
+    ref = build_ref.load()
+    if ref is None:  # the float64 port
+        out = lm_oracle.fit_batch(models.gauss2d, data, p0, "mle", xy)
+        return out["popt"], out["info"], out["nfev"]
+    import logging
+
+    logging.getLogger("dphtools.utils.lm").setLevel(logging.ERROR)
+    n = data.shape[0]
+    popt, info, nfev = np.full((n, 5), np.nan), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    for i in range(n):  # per-ROI dphtools.utils.lm.curve_fit, exactly what a user of the reference runs (lm.py:510-685)
+        try:
+            popt[i], _, infodict, _, info[i] = ref.curve_fit(models.gauss2d, xy, data[i].ravel().astype(float), p0[i].astype(float),
+                                                            jac=models.gauss2d.jac, method="mle", full_output=True)
+            nfev[i] = infodict["nfev"]
+        except RuntimeError:  # "Optimal parameters not found" from either stage
+            info[i] = 5
+    return popt, info, nfev
+
+
+def cpu_kind():
+    from oracle import build_ref
+
+    return "reference" if build_ref.available() else "port"
 
 
 def cpu_reference(data, p0, cores):
-    """Oracle port of the reference path on `cores` processes; returns (fits/s, popt, info, nfev)."""
+    """The reference path (oracle/_ref, else the oracle port) on `cores` processes; returns (fits/s, popt, info, nfev)."""
     import multiprocessing as mp
 
     chunks = [(data[i::cores], p0[i::cores]) for i in range(cores)]
@@ -118,7 +141,8 @@ def run_reference(args):
     from dphtools_b200 import synth
 
     cores = os.cpu_count()
-    per_step = max(256, 400 * cores)  # ~400 fits per core and step: ~1.5-2 s per step
+    kind = cpu_kind()
+    per_step = max(256, (100 if kind == "reference" else 400) * cores)  # ~1.5-2 s per step
     w = synth.WORKLOADS[WORKLOAD](per_step * (args.steps + args.warmup), seed=100)
     rates = []
     for s in range(args.steps + args.warmup):
@@ -133,7 +157,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * per_step / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "1e5 symmetric 2D Gaussian MLE fits, 11x11 ROIs, photons 100-5000 (configs[1]); bounded sample per step", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores, "kind": kind, "sample": sample,
+                         "what": "dphtools.utils.lm.curve_fit(method='mle') of the reference itself, per ROI (oracle/_ref)" if kind == "reference"
+                         else "float64 port oracle/lm_oracle.py (oracle/_ref not built)"},
         "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -188,9 +214,9 @@ def main():
     d_p0 = [torch.from_numpy(s["p0"]).to(dev) for s in sets]
 
 
-    def step(i, counts=False):
+    def step(i, counts=False, pipelined=False):
         return dph.curve_fit_batch(models.gauss2d, d_data[i % N_SETS], d_p0[i % N_SETS], "mle", return_counts=counts,
-                                   group_lanes=args.group_lanes)
+                                   group_lanes=args.group_lanes, pipelined=pipelined)
 
     def barrier():
         if world > 1:
@@ -205,55 +231,45 @@ def main():
     t_warm = time.perf_counter()
     i = args.warmup
     while time.perf_counter() - t_warm < 0.5:
-        step(i)
+        step(i, pipelined=True)
         i += 1
         if i % 8 == 0:
+            dph.join()
             torch.cuda.synchronize()
+    dph.join()
     barrier()
-    # K steps, timed with CUDA events on the launch stream and bracketed by barrier + synchronize, max over ranks.
-    # The block is repeated three times and the median is reported (all three are in the JSON line): the timed
-    # region is ~0.1 s long and a single host-side hiccup (scheduler, NVML query) would otherwise decide the number.
+
+    def timed_steps(pipelined):
+        """K steps, timed with CUDA events on the launch stream and bracketed by barrier + synchronize, max over ranks.
+        The block is repeated three times and the median is reported (all three are in the JSON line): the timed region
+        is ~0.1 s long and a single host-side hiccup (scheduler, NVML query) would otherwise decide the number."""
+        reps, last = [], None
+        for _ in range(3):
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(args.steps):
+                last = step(i, pipelined=pipelined)
+            if pipelined:
+                dph.join()  # the launch stream waits for every pending call: ev1 marks the end of all K steps
+            ev1.record()
+            barrier()
+            ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            reps.append(float(ms.item()))
+        return reps, last
+
+    # `value`: the K steps issued as pipelined calls (DPHLM_FLAG_PIPELINED: each call is complete work on its own buffers; the
+    # library keeps two in flight on its own streams, so the drain and the stragglers of one step run under the next) and
+    # joined before the closing event.  `serialized` below is the same with every call stream-ordered behind the previous one.
     sampler.active = True
-    repeats = []
-    for _ in range(3):
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for i in range(args.steps):
-            res = step(i)
-        ev1.record()
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        repeats.append(float(ms.item()))
+    repeats, res = timed_steps(True)
     sampler.active = False
     ms_total = float(np.median(repeats))
     value = world * n * args.steps / (ms_total * 1e-3)
-
-    # informational: the same K steps issued round-robin on two CUDA streams (two batches in flight, so the drain of one
-    # step's kernels overlaps the next step's); `value` above stays the strict one-stream figure
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    rep2 = []
-    for _ in range(3):  # median of three blocks, like `value`
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for st_ in streams:
-            st_.wait_event(ev0)
-        for i in range(args.steps):
-            with torch.cuda.stream(streams[i % 2]):
-                step(i)
-        for st_ in streams:
-            torch.cuda.current_stream().wait_stream(st_)
-        ev1.record()
-        barrier()
-        ms2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        rep2.append(float(ms2.item()))
-    ms2 = torch.tensor([float(np.median(rep2))])
-    value_two_streams = world * n * args.steps / (float(ms2.item()) * 1e-3)
+    rep_ser, _ = timed_steps(False)
+    value_serialized = world * n * args.steps / (float(np.median(rep_ser)) * 1e-3)
 
     # ---- the two kernels alone: per-launch durations (CUDA events recorded by the library on the launch
     # stream around each kernel) and algorithmic flops from the per-fit counters the kernels return
@@ -272,9 +288,32 @@ def main():
     k_pre, k_main, k_tail = float(np.mean(t_pre)), float(np.mean(t_main)), float(np.mean(t_tail))
     k_s = k_pre + k_main + k_tail  # the whole call: both main kernels and the wait for the pollers' last straggler
     flops = [a + b for a, b in zip(fl_pre, fl_main)]
-    achieved_tf = float(np.mean(fl_main)) / k_main / 1e12      # dominant kernel: the lm() loop
+    # dominant kernel: the lm() loop.  Its flops include the trips the poller finishes for it, so its time includes the wait for
+    # the pollers after the main launch (k_tail)
+    achieved_tf = float(np.mean(fl_main)) / (k_main + k_tail) / 1e12
     step_tf = float(np.mean(flops)) / k_s / 1e12               # both kernels of a step
     props = torch.cuda.get_device_properties(dev)
+    fp32_measured_tf = _lib.measure_fp32_peak()  # FFMA chains on this GPU, now
+
+    # ---- the platform's ceiling for the end-to-end figure: the bare host-to-device copy of one step's inputs from pinned
+    # memory, all ranks at once, nothing else running (GB/s per rank; the slowest rank counts)
+    h_probe = torch.from_numpy(dph.pinned_empty(n * (ROI * ROI + 5)))  # the allocator the e2e leg uses (cudaHostAlloc)
+    h_probe.zero_()
+    d_probe = torch.empty_like(h_probe, device=dev)
+    for _ in range(2):
+        d_probe.copy_(h_probe, non_blocking=True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(8):
+        d_probe.copy_(h_probe, non_blocking=True)
+    ev1.record()
+    barrier()
+    h2d_gbs = torch.tensor([8 * h_probe.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9], device=dev)
+    if world > 1:
+        dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
+    h2d_gbs = float(h2d_gbs.item())
+    del h_probe, d_probe
 
     # ---- end to end through the public API with pinned host buffers (H2D + fit + D2H per step)
     h_sets = []
@@ -333,16 +372,21 @@ def main():
             "metric": METRIC, "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "ms_per_step_repeats": [r / args.steps for r in repeats], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "two_streams": {"value": value_two_streams, "note": "informational: same steps, issued round-robin on two CUDA streams"},
+            "serialized": {"value": value_serialized, "ms_per_step": float(np.median(rep_ser)) / args.steps,
+                           "note": "informational: the same K steps without DPHLM_FLAG_PIPELINED (each call stream-ordered behind the previous one)"},
             "config": {
                 "workload": "1e5 symmetric 2D Gaussian MLE fits per GPU and step, 11x11 ROIs, photons 100-5000 (BASELINE configs[1])",
                 "fits_per_gpu_per_step": n, "sharding": "independent fits, contiguous shards, no collective",
+                "pipeline": "steps issued as pipelined calls (two in flight on the library's streams), joined before the closing event",
                 "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2" % (N_SETS, N_SETS * n * ROI * ROI * 4 / 1e6),
                 "converged_fraction": float(((info >= 1) & (info <= 4)).mean()),
             },
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": n * (ROI * ROI + 5) * 4,
                     "d2h_bytes_per_step": n * (5 + 3) * 4, "steps": e2e_steps, "host_memory": "pinned inputs and outputs (dphtools_b200.pinned_empty)",
                     "converged_fraction": float(((r_host.info >= 1) & (r_host.info <= 4)).mean()),
+                    "h2d_probe": {"gbs_per_rank": h2d_gbs, "ceiling_fits_per_s": world * h2d_gbs * 1e9 / ((ROI * ROI + 5) * 4),
+                                  "frac_of_ceiling": e2e_value / (world * h2d_gbs * 1e9 / ((ROI * ROI + 5) * 4)),
+                                  "note": "bare pinned host-to-device copy of one step's inputs, all ranks at once (slowest rank): what the platform allows end to end"},
                     "uint16_input": {"value": e2e_u16, "h2d_bytes_per_step": n * (ROI * ROI * 2 + 5 * 4),
                                      "note": "informational: same call with uint16 camera counts as host input"}},
             "gpu_launches": 4 * args.steps,  # pre-fit + lm() main launches and their two straggler follow-ups
@@ -351,7 +395,10 @@ def main():
                 # dram__bytes_read+write of the lm() main launch from the ncu --set full capture of this workload
                 # (profiles/r1_ncu_full_v4_gauss2d_11x11_G4.txt); algorithmic: 484 B/fit read again + 32 B/fit written
                 "traffic": 51.2e6 * n / 1e5, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; the main launch, events around it)",
-                "kernel_ms": k_main * 1e3, "share_of_step": k_main / k_s,
+                "kernel_ms": k_main * 1e3, "stage_ms": (k_main + k_tail) * 1e3, "share_of_step": (k_main + k_tail) / k_s,
+                "timing_note": "kernel times come from calls with DPHLM_FLAG_TIMING: events between the launches, so the lm() kernel does not "
+                               "start early in the slots the pre-fit kernel frees, and nothing is pipelined; `achieved` = lm() flops / stage_ms",
+                "peak_measured": fp32_measured_tf, "frac_of_measured": achieved_tf / fp32_measured_tf,
                 "straggler_tail_ms": k_tail * 1e3,  # after the lm() kernel: the pollers finishing the longest straggler (mean over the input sets)
                 "peak_source": "SMs x 128 lanes x 2 x max SM clock (no fp32 entry in MEASURED_PEAKS.json)",
                 "flops_per_fit": float(np.mean(fl_main)) / n,
@@ -366,7 +413,8 @@ def main():
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count()
-            n_cpu = max(256, 40 * cores)
+            kind = cpu_kind()
+            n_cpu = max(256, (250 if kind == "reference" else 40) * cores)
             rate, popt_ref, info_ref, nfev_ref = cpu_reference(sets[0]["data"][:n_cpu], sets[0]["p0"][:n_cpu], cores)
             r0 = step(0)
             torch.cuda.synchronize()
@@ -374,8 +422,10 @@ def main():
 
             rep = parity_report("gauss2d", dict(popt=r0.popt[:n_cpu].cpu().numpy(), info=r0.info[:n_cpu].cpu().numpy(),
                                                 nfev=r0.nfev[:n_cpu].cpu().numpy()), dict(popt=popt_ref, info=info_ref, nfev=nfev_ref))
-            out["cpu_baseline"] = {"value": rate, "unit": "fits/s", "cores": cores, "kind": "port",
-                                   "sample": "first %d ROIs of input set 0, float64 oracle port of curve_fit(method='mle'), one process per core" % n_cpu,
+            what = ("the reference's own dphtools.utils.lm.curve_fit(method='mle') per ROI (oracle/_ref)" if kind == "reference"
+                    else "float64 oracle port of curve_fit(method='mle') (oracle/_ref not built)")
+            out["cpu_baseline"] = {"value": rate, "unit": "fits/s", "cores": cores, "kind": kind,
+                                   "sample": "first %d ROIs of input set 0, %s, one process per core" % (n_cpu, what),
                                    "parity_on_sample": rep}
         print(json.dumps(out))
     if world > 1:

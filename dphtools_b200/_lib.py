@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("DPHLM_LIB") or os.path.join(os.path.dirname(os.path.a
 SYMBOLS = [
     "dphlm_desc_init", "dphlm_fit_batch", "dphlm_fit_batch_host", "dphlm_host_alloc", "dphlm_host_free",
     "dphlm_device_count", "dphlm_version", "dphlm_last_error", "dphlm_last_kernel_ms", "dphlm_covariance", "dphlm_extract_rois",
+    "dphlm_join", "dphlm_call_status", "dphlm_measure_fp32_peak",
 ]
 
 
@@ -71,6 +72,12 @@ def lib():
         L.dphlm_device_count.restype = ctypes.c_int
         L.dphlm_last_kernel_ms.argtypes = [ctypes.POINTER(ctypes.c_float * 3)]
         L.dphlm_last_kernel_ms.restype = ctypes.c_int
+        L.dphlm_join.argtypes = [ctypes.c_void_p]
+        L.dphlm_join.restype = ctypes.c_int
+        L.dphlm_call_status.argtypes = [ctypes.POINTER(ctypes.c_int)]
+        L.dphlm_call_status.restype = ctypes.c_int
+        L.dphlm_measure_fp32_peak.argtypes = [ctypes.POINTER(ctypes.c_double)]
+        L.dphlm_measure_fp32_peak.restype = ctypes.c_int
         L.dphlm_version.restype = ctypes.c_int
         L.dphlm_last_error.restype = ctypes.c_char_p
         _lib = L
@@ -80,6 +87,9 @@ def lib():
 FLAG_TIMING = 1
 FLAG_NO_HANDOFF = 2
 FLAG_DATA_U16 = 4
+FLAG_PIPELINED = 8
+FLAG_SKIP_PREFIT = 16
+INFO_UNFINISHED = -2139062144  # DPHLM_INFO_UNFINISHED
 
 
 def last_kernel_ms():
@@ -93,3 +103,11 @@ def last_kernel_ms():
 
 def last_error():
     return lib().dphlm_last_error().decode()
+
+
+def measure_fp32_peak():
+    """Measured FP32 FFMA throughput of the current device, TFLOP/s."""
+    v = ctypes.c_double(0.0)
+    if lib().dphlm_measure_fp32_peak(ctypes.byref(v)) != 0:
+        raise RuntimeError("dphlm: " + last_error())
+    return float(v.value)

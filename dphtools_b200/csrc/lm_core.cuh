@@ -36,6 +36,9 @@
 #ifndef DPH_GAUSS2D_STORE
 #define DPH_GAUSS2D_STORE false
 #endif
+#ifndef DPH_TIE_BREAK
+#define DPH_TIE_BREAK 0  // float64 gradient for xtol ties (precise_gradient): experimental, off
+#endif
 #ifndef DPH_PAIR_UNROLL
 #define DPH_PAIR_UNROLL 1  // unroll factor of the pixel-pair loop (registers vs instruction-level parallelism)
 #endif
@@ -176,6 +179,35 @@ DPH_HD T expm1_small(T a) {
 }
 constexpr float kSmallArg = 0.0625f;
 
+// Chi-square differences of the branch-free pass, expanded about the ACCEPTED point.  With f0 the model value there,
+// u = (f1 - f0) / f0 and the Poisson term t(f) = f - y ln f:
+//   t(f0) - t(f1) = (y/f0 - 1) (f1 - f0) - y u^2 S(u),     S(u) = 1/2 - u/3 + u^2/4 - ...   (u - ln(1 + u) = u^2 S(u))
+// The first-order term uses the very residual 1 - y/f0 the gradient at the accepted point was summed from (same inputs, same
+// instructions), so first-order term and step stay consistent down to rounding: that, not the accuracy of the logarithm,
+// is what keeps the signs of reductions ~1e-9 of chi-square right.  The series is cut where its truncation stays below
+// what the lg2-based form delivers at the switch point |u| = 1/8 (u^7/7 = 7e-8 absolute); beyond it -- a step that changes
+// a pixel's model value by more than 12 % -- a rarely taken branch substitutes the logarithm.
+constexpr float kSeriesMax = 0.125f;
+template <class T>
+DPH_HD T series_ln(T u) {  // S(u), degree 4
+    T p = T(1.0f / 6.0f);
+    p = f_fma(p, u, T(-0.2f));
+    p = f_fma(p, u, T(0.25f));
+    p = f_fma(p, u, T(-1.0f / 3.0f));
+    return f_fma(p, u, T(0.5f));
+}
+template <class T>
+DPH_HD T series_ln3(T u) {  // S(u), degree 3 (the predicted reduction is only compared with the actual one at the 1 % level)
+    T p = T(-0.2f);
+    p = f_fma(p, u, T(0.25f));
+    p = f_fma(p, u, T(-1.0f / 3.0f));
+    return f_fma(p, u, T(0.5f));
+}
+DPH_HD float v_absmax(float a, float b) { return fmaxf(fabsf(a), fabsf(b)); }
+DPH_HD float v_absmax(f2 a, f2 b) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))); }
+DPH_HD float v_absmax(float a) { return fabsf(a); }
+DPH_HD float v_absmax(f2 a) { return fmaxf(fabsf(a.x), fabsf(a.y)); }
+
 // ------------------------------------------------------------------------------- small dense algebra
 // packed upper triangle, row-major: (i,j), i <= j
 template <int P>
@@ -290,6 +322,13 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
         T t = e[0] * T(q.as2);
         J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = e[0] * T(q.as3) * g.r2; J[4] = T(1.0f);
     }
+    // float64 model value and Jacobian row at one pixel (the tie-break pass of StageB, see precise_gradient)
+    DPH_HD static void eval64(const double* p, const float*, double cx, double cy, double& f, double* J) {
+        const double dx = cx - p[1], dy = cy - p[2], r2 = dx * dx + dy * dy, s2 = p[3] * p[3];
+        const double e = exp(-r2 / (2.0 * s2)), ae = p[0] * e;
+        f = ae + p[4];
+        J[0] = e; J[1] = ae * dx / s2; J[2] = ae * dy / s2; J[3] = ae * r2 / (s2 * p[3]); J[4] = 1.0;
+    }
     DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
         s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d4 = d[4];
         s.nh1 = -0.5f * b.s2;                                             // -1/(2 sigma_new^2)
@@ -347,6 +386,13 @@ struct Gauss2DFixed {
     template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
         T t = e[0] * T(q.as2);
         J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = T(1.0f);
+    }
+    DPH_HD static void eval64(const double* p, const float* consts, double cx, double cy, double& f, double* J) {
+        const double sig = consts ? double(consts[0]) : 1.0;
+        const double dx = cx - p[1], dy = cy - p[2], r2 = dx * dx + dy * dy, s2 = sig * sig;
+        const double e = exp(-r2 / (2.0 * s2)), ae = p[0] * e;
+        f = ae + p[3];
+        J[0] = e; J[1] = ae * dx / s2; J[2] = ae * dy / s2; J[3] = 1.0;
     }
     DPH_HD static void prepare_step(const Par& a, const Par&, const float* d, Step& s) {
         s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3];
@@ -409,6 +455,14 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         J[4] = ae * g.v * vay * T(q.isy);
         J[5] = ae * g.u * g.v * T(q.ay - q.ax);
         J[6] = T(1.0f);
+    }
+    DPH_HD static void eval64(const double* p, const float*, double cx, double cy, double& f, double* J) {
+        const double c = cos(p[5]), s = sin(p[5]), dx = cx - p[1], dy = cy - p[2];
+        const double u = c * dx + s * dy, v = -s * dx + c * dy, ax = 1.0 / (p[3] * p[3]), ay = 1.0 / (p[4] * p[4]);
+        const double e = exp(-0.5 * (u * u * ax + v * v * ay)), ae = p[0] * e;
+        f = ae + p[6];
+        J[0] = e; J[1] = ae * (u * ax * c - v * ay * s); J[2] = ae * (u * ax * s + v * ay * c);
+        J[3] = ae * u * u * ax / p[3]; J[4] = ae * v * v * ay / p[4]; J[5] = ae * u * v * (ay - ax); J[6] = 1.0;
     }
     DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
         s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3]; s.d4 = d[4]; s.d5 = d[5]; s.d6 = d[6];
@@ -559,6 +613,24 @@ struct Gauss2DIntegratedT {
         if (!FIXED) J[3] = f_fma(g.sex, g.ey, g.ex * g.sey) * T(q.amp);
         J[kOff] = T(1.0f);
     }
+    DPH_HD static void axis64(double t, double sig, double& e, double& de, double& se) {
+        const double a = 0.70710678118654752440 / sig, c = 0.39894228040143267794 / sig;
+        const double tp = t + 0.5, tm = t - 0.5, zp = tp * a, zm = tm * a;
+        e = 0.5 * (erf(zp) - erf(zm));
+        const double gp = exp(-zp * zp), gm = exp(-zm * zm);
+        de = c * (gm - gp);
+        se = c / sig * (tm * gm - tp * gp);
+    }
+    DPH_HD static void eval64(const double* p, const float* consts, double cx, double cy, double& f, double* J) {
+        const double sig = FIXED ? (consts ? double(consts[0]) : 1.0) : p[3];
+        double ex, dex, sex, ey, dey, sey;
+        axis64(cx - p[1], sig, ex, dex, sex);
+        axis64(cy - p[2], sig, ey, dey, sey);
+        f = p[0] * ex * ey + p[kOff];
+        J[0] = ex * ey; J[1] = p[0] * dex * ey; J[2] = p[0] * ex * dey;
+        if (!FIXED) J[3] = p[0] * (sex * ey + ex * sey);
+        J[kOff] = 1.0;
+    }
     DPH_HD static void prepare_step(const Par& a, const Par&, const float* d, Step& s) {
 #pragma unroll
         for (int k = 0; k < P; ++k) s.d[k] = d[k];
@@ -615,6 +687,16 @@ struct MultiExp {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[i]; J[2 * i + 1] = g.x * e[i] * T(-q.a[i]); }
         if (OFFSET) J[2 * NEXP] = T(1.0f);
+    }
+    DPH_HD static void eval64(const double* p, const float*, double cx, double, double& f, double* J) {
+        f = OFFSET ? p[2 * NEXP] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) {
+            const double e = exp(-p[2 * i + 1] * cx);
+            f += p[2 * i] * e;
+            J[2 * i] = e; J[2 * i + 1] = -p[2 * i] * cx * e;
+        }
+        if (OFFSET) J[2 * NEXP] = 1.0;
     }
     DPH_HD static void prepare_step(const Par&, const Par&, const float* d, Step& s) {
 #pragma unroll
@@ -751,6 +833,26 @@ struct MultiExpIrf {
         for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[2 * i]; J[2 * i + 1] = e[2 * i + 1] * T(-q.a[i]); }
         if (OFFSET) J[2 * NEXP] = T(1.0f);
     }
+    // cy carries the bin index; consts = [W, m0, dt, irf...]
+    DPH_HD static void eval64(const double* p, const float* consts, double, double cy, double& f, double* J) {
+        f = OFFSET ? p[2 * NEXP] : 0.0;
+        if (OFFSET) J[2 * NEXP] = 1.0;
+        const int W = consts ? int(fminf(fmaxf(consts[0], 1.0f), float(kIrfTaps))) : 1;
+        const double m0 = consts ? double(consts[1]) : 0.0, dt = consts ? double(consts[2]) : 1.0;
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) {
+            double c = 0.0, d = 0.0;
+            for (int q = 0; q < W; ++q) {
+                const double lag = (cy - m0 - double(q)) * dt;
+                if (lag >= 0.0) {
+                    const double term = double(consts[3 + q]) * exp(-p[2 * i + 1] * lag);
+                    c += term; d += term * lag;
+                }
+            }
+            f += p[2 * i] * c;
+            J[2 * i] = c; J[2 * i + 1] = -p[2 * i] * d;
+        }
+    }
     DPH_HD static void prepare_step(const Par&, const Par&, const float* d, Step& s) {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) { s.da[i] = d[2 * i]; s.dk[i] = d[2 * i + 1]; }
@@ -813,10 +915,16 @@ struct Lanes {
         return v;
     }
     DPH_HD static bool warp_any(bool v) { return __any_sync(0xffffffffu, v); }
+    DPH_HD double sum_group(double v) const {  // only the lanes of this group take part (group-divergent code)
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+        return v;
+    }
     DPH_HD float up(float v, int o) const { return __shfl_up_sync(gmask, v, o, G); }   // value of lane - o (own value below o)
     DPH_HD float bcast(float v, int src) const { return __shfl_sync(gmask, v, src, G); }  // value of group lane src
     DPH_HD void sync() const { __syncwarp(gmask); }
 #else
+    DPH_HD double sum_group(double v) const { return v; }
     DPH_HD float up(float v, int) const { return v; }
     DPH_HD float bcast(float v, int) const { return v; }
     DPH_HD void sync() const {}
@@ -906,8 +1014,8 @@ DPH_HD void mle_weights(float f, float y, float& w, float& res) {
 
 // One pixel (T = float) or one pair of adjacent pixels (T = f2) of the regular, branch-free trial
 // evaluation: model at the trial point q1 = q0 + d, the chi-square reductions from per-pixel differences
-// and, speculatively, the normal equations at the trial point.  QUIRK (lm.py:446-449): the predicted
-// model is f(x_new) + J(x_old) d.
+// (see series_ln) and, speculatively, the normal equations at the trial point.  QUIRK (lm.py:446-449): the
+// predicted model is f(x_new) + J(x_old) d.
 template <class Mo, bool MLE, bool PRED, class T>
 DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1, const typename Mo::Step& st, bool init,
                           bool want_chi, T cx, T cy, T y, const T* e0in, T* e1, Acc<Mo::P, T>& n) {
@@ -934,15 +1042,26 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
         // (tracked in n.lo; the clamp turns a NaN into a 0 that the minimum sees).  So 1 + u = f_new / f_old > 0 where it counts.
         const T f1c = v_max(f1, 0.0f);
         const T rf0 = v_rcp(f0);
-        n.actual = f_fma(y, log1p_pos(dl * rf0), n.actual) - dl;
+        const T yf0 = y * rf0;
+        const T rn0 = yf0 - T(1.0f);  // -(1 - y/f0): minus the residual the gradient at the accepted point was summed from
+        const T u = dl * rf0;
+        T sa = (yf0 * dl) * u * series_ln(u);  // y (u - ln(1 + u))
         if (PRED) {
             const T jd = Mo::jdx(q0, st, df, e0);
             const T dp = dl + jd;
+            const T up = dp * rf0;
+            T sp = (yf0 * dp) * up * series_ln3(up);
+            if (v_absmax(u, up) > kSeriesMax) {  // a step that changes this pixel by more than 12 %: rare
+                sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(-kLn2), u));
+                sp = v_sel_small(up, kSeriesMax, sp, y * f_fma(v_lg2(up + T(1.0f)), T(-kLn2), up));
+            }
             n.lo = v_min3(n.lo, f1c, f1c + jd);
-            n.predicted = f_fma(y, log1p_pos(dp * rf0), n.predicted) - dp;
+            n.predicted = f_fma(rn0, dp, n.predicted) - sp;
         } else {
+            if (v_absmax(u) > kSeriesMax) sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(-kLn2), u));
             n.lo = v_min3(n.lo, f1c, f1c);
         }
+        n.actual = f_fma(rn0, dl, n.actual) - sa;
         const T rf1 = v_rcp(f1c);
         const T yf = y * rf1;
         n.add(J, yf * rf1, T(1.0f) - yf);
@@ -1094,6 +1213,41 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
     if (!MLE && !f_finite(n.chi1)) n.flags |= kFlagNonFinite;
 }
 
+// ---------------------------------------------------------------------------------- tie-break pass
+// The reference ends lm() with info = 2 when |dx| <= xtol (|x| + xtol) with xtol = 1.49e-8 (lm.py:365-367, 430-432): a
+// step four times smaller than float32 resolves in x itself.  Whether that test fires is decided by the gradient at the
+// accepted point to ~1e-9 of its scale, which neither a float32 x (rounding the accepted point moves the Newton step by the
+// rounding error) nor a float32 model value (ex2.approx alone is 2e-7) can deliver; left alone, the fits whose last step is
+// within a factor ~8 of the threshold -- 1-3 % of a batch -- get a coin flip between info 1 and info 2.  For exactly those
+// trips, and only for them, the gradient is recomputed in float64 at the accepted point kept as a float32 pair (x + xlo, the
+// rounding error of x <- x + d is kept), and the test is repeated with the step from that gradient.  This is the one place
+// float64 is used; it costs one extra pass for ~2 % of the fits and nothing otherwise.
+template <class Mo, bool MLE, int G>
+DPH_HD void precise_gradient(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const float* x, const float* xlo, const float* consts,
+                             double* g) {
+    constexpr int P = Mo::P;
+    double p[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) { p[k] = double(x[k]) + double(xlo[k]); g[k] = 0.0; }
+    for (int i = ln.lane; i < px.M; i += G) {
+        double f, J[P];
+        Mo::eval64(p, consts, double(px.cx[i]), double(px.cy[i]), f, J);
+        const double y = double(px.y[i]);  // MLE: clamped when the fit was staged (lm.py:127)
+        double res;
+        if (MLE) {
+            if (f <= 0.0) f = 0.0;  // lm.py:132
+            const double yf = y / f, yf2 = yf / f;
+            res = (yf - yf == 0.0 && yf2 - yf2 == 0.0) ? 1.0 - yf : 1.0;  // lm.py:86-102: invalid pixel -> residual 1
+        } else {
+            res = f - y;
+        }
+#pragma unroll
+        for (int k = 0; k < P; ++k) g[k] += J[k] * res;
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k) g[k] = ln.sum_group(g[k]);
+}
+
 // ------------------------------------------------------------------------------------- options/result
 struct Options {
     float ftol, xtol, gtol, factor;
@@ -1174,7 +1328,7 @@ template <class Mo>
 struct StageA {
     static constexpr int P = Mo::P;
     static constexpr int NTP = NT<P>::value;
-    static constexpr bool kMle = false, kPred = false;
+    static constexpr bool kMle = false, kPred = false, kTie = false;
     float x[P], A[NTP], g[P], D[P];
     typename Mo::Par q0;
     float chi;  // 0.5 * fnorm^2
@@ -1213,17 +1367,19 @@ struct StageA {
         init = true; resumed = true;
     }
     DPH_HD bool wants_chi() const { return false; }
-    // returns false when the fit ended without needing the pass
-    DPH_HD bool propose(const Options&, float* p) {
+    // 0: the fit ended without needing the pass, 1: evaluate x + p (2, stage B only: tie-break wanted)
+    DPH_HD int propose(const Options&, float* p) {
         if (init) {
 #pragma unroll
             for (int i = 0; i < P; ++i) p[i] = 0.0f;
-            return true;
+            return 1;
         }
         lmpar_normal<P>(A, g, D, delta, par, p, pnorm);
         if (first) delta = fminf(delta, pnorm);
-        return true;
+        return 1;
     }
+    DPH_HD int propose_precise(const Options&, const double*, float*) { return 1; }
+    DPH_HD const float* xlo_ptr() const { return x; }
     // new Jacobian at an accepted point: gradient test and rescaling (lmder.f: gnorm, diag = max(diag, wa2))
     DPH_HD void fresh(const Options& opt) {
         if (opt.gtol > 0.0f && chi > 0.0f) {
@@ -1324,7 +1480,9 @@ struct StageB {
     static constexpr int P = Mo::P;
     static constexpr int NTP = NT<P>::value;
     static constexpr bool kMle = MLE, kPred = true;
-    float x[P], A[NTP], g[P], dtd[P], xret[P];
+    static constexpr bool kTie = MLE && DPH_TIE_BREAK;  // least squares ends at trip 0 on the pre-fit's own optimum (Q16): nothing to break
+    static constexpr float kTieBand = 8.0f;  // |dx| within this factor of the xtol threshold -> float64 gradient (precise_gradient)
+    float x[P], xlo[P], A[NTP], g[P], dtd[P], xret[P];
     typename Mo::Par q0;
     float chisq_old, chisq_ret, lam;
     int info, ev, n_acc, n_rej;
@@ -1332,7 +1490,7 @@ struct StageB {
 
     DPH_HD void start(const float* p_ls, const float* consts = nullptr) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) x[i] = xret[i] = p_ls[i];
+        for (int i = 0; i < P; ++i) { x[i] = xret[i] = p_ls[i]; xlo[i] = 0.0f; }
         Mo::set_consts(q0, consts);
         Mo::prepare(x, q0);
         chisq_old = chisq_ret = lam = 0.0f;
@@ -1349,7 +1507,7 @@ struct StageB {
     }
     DPH_HD void resume(const float* r, const float* consts = nullptr) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) { x[i] = r[i]; dtd[i] = r[P + i]; xret[i] = r[2 * P + i]; }
+        for (int i = 0; i < P; ++i) { x[i] = r[i]; dtd[i] = r[P + i]; xret[i] = r[2 * P + i]; xlo[i] = 0.0f; }
         chisq_old = r[3 * P]; chisq_ret = r[3 * P + 1]; lam = r[3 * P + 2];
         ev = int(r[3 * P + 3]); n_acc = int(r[3 * P + 4]); n_rej = int(r[3 * P + 5]);
         Mo::set_consts(q0, consts);
@@ -1358,39 +1516,58 @@ struct StageB {
         init = true; live = false; resumed = true;
     }
     DPH_HD bool wants_chi() const { return init && !resumed; }
-    DPH_HD bool propose(const Options& opt, float* p) {
+    // 0: the fit ended before the evaluation (xtest / gtest), 1: evaluate x + p, 2: |dx| is within kTieBand of the xtol
+    // threshold -- the caller supplies the float64 gradient and calls propose_precise()
+    DPH_HD int propose(const Options& opt, float* p) {
         live = false;
 #pragma unroll
         for (int i = 0; i < P; ++i) p[i] = 0.0f;
-        if (init) return true;
+        if (init) return 1;
         if (opt.gtol > 0.0f) {  // lm.py:358-363, 409-411
             float gm = 0.0f;
 #pragma unroll
             for (int i = 0; i < P; ++i) gm = fmaxf(gm, fabsf(g[i]));
-            if (gm <= opt.gtol) { info = 4; return false; }
+            if (gm <= opt.gtol) { info = 4; return 0; }
         }
+        return solve_step(opt, g, p, kTie);
+    }
+    DPH_HD int propose_precise(const Options& opt, const double* g64, float* p) {
+        float gp[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) gp[i] = float(g64[i]);
+        const int r = solve_step(opt, gp, p, false);
+        if (r == 1 && live) {  // the step starts at x + xlo
+#pragma unroll
+            for (int i = 0; i < P; ++i) p[i] += xlo[i];
+        }
+        return r;
+    }
+    DPH_HD const float* xlo_ptr() const { return xlo; }
+    DPH_HD int solve_step(const Options& opt, const float* gg, float* p, bool tie) {
         float U[NTP], d[P];
         bool ok = chol_factor<P>(A, dtd, lam, U);
         if (ok) {
-            chol_solve_neg<P>(U, g, d);
+            chol_solve_neg<P>(U, gg, d);
 #pragma unroll
             for (int i = 0; i < P; ++i) ok = ok && f_finite(d[i]);
         }
         if (!ok) {
             lam *= opt.factor;  // lm.py:426-428: the trip is consumed
-            return true;
+            return 1;
         }
         float dn = 0.0f, xn2 = 0.0f;
 #pragma unroll
         for (int i = 0; i < P; ++i) { dn = f_fma(d[i], d[i], dn); xn2 = f_fma(x[i], x[i], xn2); }
-        if (sqrtf(dn) <= opt.xtol * (sqrtf(xn2) + opt.xtol)) {  // lm.py:365-367, 430-432
+        const float thr = opt.xtol * (sqrtf(xn2) + opt.xtol), dnorm = sqrtf(dn);
+        if (tie && dnorm <= kTieBand * thr && dnorm * kTieBand >= thr) return 2;
+        if (dnorm <= thr) {  // lm.py:365-367, 430-432
             info = 2;
-            return false;
+            return 0;
         }
         live = true;
 #pragma unroll
         for (int i = 0; i < P; ++i) p[i] = d[i];
-        return true;
+        return 1;
     }
     DPH_HD bool consume(const Options& opt, const Normal<P>& n, const float* p, const typename Mo::Par& q1, bool& accepted) {
         const int maxfev = opt.maxfev > 0 ? opt.maxfev : 100 * (P + 1);
@@ -1436,7 +1613,11 @@ struct StageB {
                     return true;
                 }
 #pragma unroll
-                for (int i = 0; i < P; ++i) x[i] = xret[i];
+                for (int i = 0; i < P; ++i) {  // x <- fl(x + p); xlo = (x + p) - fl(x + p) exactly (TwoSum)
+                    const float sum = xret[i], bv = sum - x[i];
+                    if (kTie) xlo[i] = (x[i] - (sum - bv)) + (p[i] - bv);
+                    x[i] = sum;
+                }
                 q0 = q1;
                 accepted = true;
                 chisq_old -= actual;
@@ -1492,7 +1673,15 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         }
         if (!Lanes<G>::warp_any(has)) break;
         bool pass = has;
-        if (has && !st.propose(opt, p)) {  // ended before the evaluation (xtest / gtest)
+        int proposed = has ? st.propose(opt, p) : 1;
+        if (Stage::kTie && Lanes<G>::warp_any(proposed == 2)) {  // xtol tie-break: rare (see precise_gradient)
+            if (proposed == 2) {
+                double g64[P];
+                precise_gradient<Mo, Stage::kMle, G>(ln, px, st.x, st.xlo_ptr(), io.consts(), g64);
+                proposed = st.propose_precise(opt, g64, p);
+            }
+        }
+        if (has && proposed == 0) {  // ended before the evaluation (xtest / gtest)
             io.store(ln, st, fit);
             has = false;
             pass = false;

@@ -37,6 +37,8 @@ int get_ctx(int dev, DeviceCtx** out) {
         cudaMemPool_t pool;
         unsigned long long keep = ~0ull;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        CUDA_TRY(cudaMalloc(&c.err_word, sizeof(int)));
+        CUDA_TRY(cudaMemset(c.err_word, 0, sizeof(int)));
     }
     *out = &c;
     return 0;
@@ -53,12 +55,14 @@ int model_consts(int model, const float* consts) {
     return 0;
 }
 
-int auto_group(int M, int model, long long n_fits) {
+int auto_group(int M, int model, long long n_fits, bool tail_hidden) {
     // measured on B200 (profiles/): 7x7 -> 2 lanes; 11x11 -> 4, and 2 for the sampled Gaussian from 3e5 fits per call on (5 %
     // faster there: the per-trip scalar work is shared by 16 fits; equal at 1e5, where the longer per-fit latency shows in the
     // tails); 15x15 -> 4 for the sampled Gaussian, which keeps no per-pixel state in shared memory, 8 otherwise; 256 bins -> 16
+    if (model == DPHLM_MULTI_EXP_IRF) return M <= 512 ? 16 : 32;  // built for wide groups only (lm_inst_mexp_irf.cu)
     if (M <= 64) return 2;
-    if (M <= 128) return model == DPHLM_GAUSS2D && n_fits >= 300000 ? 2 : 4;
+    // (pipelined calls hide the tail under the next call: 2 lanes win from 1e5 fits on, 1.12e8 against 1.04e8 fits/s)
+    if (M <= 128) return model == DPHLM_GAUSS2D && (n_fits >= 300000 || (tail_hidden && n_fits >= 50000)) ? 2 : 4;
     if (M <= 240) return model == DPHLM_GAUSS2D ? 4 : 8;
     return 16;
 }
@@ -146,6 +150,18 @@ int widen_async(const void* in, float* out, long long n, cudaStream_t s) {
 }
 
 
+// One launch prepares a call: the pre-fit exit codes (0 = "not published yet" for an lm() kernel that starts early; 1 when the
+// pre-fit is skipped), the header and ready flags of the straggler lists (0), the pre-fit parameters (NaN = not published)
+// and every fit's `info` (DPHLM_INFO_UNFINISHED, so that a fit nobody finished cannot be mistaken for a result).
+__global__ void dphlm_init_kernel(int* ier, int ier_value, long long n_fits, int* zero, long long n_zero, unsigned* p_ls, long long n_pls,
+                                  int* info) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = t; i < n_fits; i += stride) { ier[i] = ier_value; info[i] = DPHLM_INFO_UNFINISHED; }
+    for (long long i = t; i < n_zero; i += stride) zero[i] = 0;
+    for (long long i = t; i < n_pls; i += stride) p_ls[i] = 0xffffffffu;
+}
+
 int launch_model(const dphlm_desc* d, int G, const KArgs& a, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t s) {
     const bool mle = d->method == DPHLM_MLE;
     switch (d->model) {
@@ -180,7 +196,7 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
         a.ev = g_timing.ev;
         g_timing.valid = true;
     }
-    const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w, d->model, d->n_fits);
+    const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w, d->model, d->n_fits, d->flags & DPHLM_FLAG_PIPELINED);
     // workspace: pre-fit exit codes, and the pre-fit parameters when the caller does not want them
     const size_t b_ier = ((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255);
     const size_t b_park = park_bytes(d->n_fits);
@@ -205,8 +221,19 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     pl.ready = reinterpret_cast<int*>(ws + b_ier + 256);
     pl.rec = reinterpret_cast<float*>(ws + b_ier + 256 + park_ready_bytes(d->n_fits));
     // the pre-fit results start as "not published yet" (exit code 0, parameters NaN) for an lm() kernel that starts early
-    CUDA_TRY(cudaMemsetAsync(a.p_ls, 0xFF, (size_t)d->n_fits * d->n_param * sizeof(float), s));
-    CUDA_TRY(cudaMemsetAsync(ws, 0, b_ier + 256 + (pl.cap ? park_ready_bytes(d->n_fits) : 0), s));
+    const bool skip = d->flags & DPHLM_FLAG_SKIP_PREFIT;
+    a.skip_prefit = skip ? 1 : 0;
+    if (skip) a.p_ls = const_cast<float*>(d->p0);  // lm() alone starts from p0 (nothing writes p_ls then)
+    {
+        const long long n_zero = (long long)((256 + (pl.cap ? park_ready_bytes(d->n_fits) : 0)) / sizeof(int));
+        const long long n_pls = skip ? 0 : d->n_fits * d->n_param;
+        long long blocks = (std::max<long long>(d->n_fits, n_pls) + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        dphlm_init_kernel<<<(unsigned)blocks, 256, 0, s>>>(a.ier, skip ? 1 : 0, d->n_fits, reinterpret_cast<int*>(ws + b_ier), n_zero,
+                                                          reinterpret_cast<unsigned*>(skip ? nullptr : a.p_ls), n_pls, d->info);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { if (!ws_in) cudaFreeAsync(ws, s); return fail(std::string("init kernel: ") + cudaGetErrorString(e)); }
+    }
     int rc;
     {
         std::lock_guard<std::mutex> lk(ctx->fork_mu);  // the side stream and its events are shared per device
@@ -218,12 +245,34 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
             }
         }
         rc = launch_model(d, G, a, pl, ctx, s);
+        if (rc) {
+            // a launch failed part-way: straggler kernels may already be running on the side streams and use the workspace.
+            // Let them end (their producers never started, so they leave at once) before the workspace goes back to the pool.
+            for (auto& sd : ctx->sides) { cudaStreamSynchronize(sd.stream_a); cudaStreamSynchronize(sd.stream_b); }
+        }
     }
     if (!ws_in) cudaFreeAsync(ws, s);
     return rc;
 }
 
 size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+// FP32 pipe microbenchmark: independent scalar FFMA chains (two invariant operands), the fastest fp32 instruction stream
+// this part sustains (scripts/microbench/pipes.cu: 0.97 FFMA per clock and scheduler; packed FFMA2 issues every 2.2 clocks).
+__global__ void __launch_bounds__(256) dphlm_ffma_chain_kernel(float* out, int iters, float a, float b) {
+    float acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = threadIdx.x * 1e-3f + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = __fmaf_rn(acc[k], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += acc[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 
 }  // namespace
 
@@ -248,7 +297,55 @@ int dphlm_fit_batch(const dphlm_desc* d_in, void* stream) {
     CUDA_TRY(cudaGetDevice(&dev));
     DeviceCtx* ctx;
     if (get_ctx(dev, &ctx)) return -1;
-    return fit_device(d, ctx, static_cast<cudaStream_t>(stream));
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    if (!(d->flags & DPHLM_FLAG_PIPELINED) || d->n_fits == 0) return fit_device(d, ctx, user);
+    // Pipelined: the whole call goes to one of the library's own streams, behind what the caller's stream holds now; the
+    // caller's stream does not wait (dphlm_join).  Consecutive calls alternate between the streams, so the drain and the
+    // stragglers of one call run under the main kernels of the next.
+    tuned.flags &= ~DPHLM_FLAG_TIMING;  // the timing events assume one call at a time on the caller's stream
+    std::lock_guard<std::mutex> lk(ctx->pipe_mu);
+    int depth = 2;
+    if (const char* e = getenv("DPHLM_PIPE_DEPTH")) depth = std::min(std::max(atoi(e), 1), (int)DeviceCtx::kPipeMax);  // tuning aid
+    DeviceCtx::Pipe& pp = ctx->pipes[ctx->next_pipe++ % depth];
+    if (!pp.stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&pp.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&pp.in_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&pp.done_ev, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(pp.in_ev, user));
+    CUDA_TRY(cudaStreamWaitEvent(pp.stream, pp.in_ev, 0));
+    const int rc = fit_device(d, ctx, pp.stream);
+    CUDA_TRY(cudaEventRecord(pp.done_ev, pp.stream));
+    pp.pending = true;
+    return rc;
+}
+
+int dphlm_join(void* stream) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DeviceCtx* ctx;
+    if (get_ctx(dev, &ctx)) return -1;
+    std::lock_guard<std::mutex> lk(ctx->pipe_mu);
+    for (auto& pp : ctx->pipes) {
+        if (!pp.pending) continue;
+        CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), pp.done_ev, 0));
+        pp.pending = false;
+    }
+    return 0;
+}
+
+int dphlm_call_status(int* tripped) {
+    if (!tripped) return fail("null pointer");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DeviceCtx* ctx;
+    if (get_ctx(dev, &ctx)) return -1;
+    CUDA_TRY(cudaDeviceSynchronize());
+    int word = 0;
+    CUDA_TRY(cudaMemcpy(&word, ctx->err_word, sizeof(int), cudaMemcpyDeviceToHost));
+    if (word) CUDA_TRY(cudaMemset(ctx->err_word, 0, sizeof(int)));
+    *tripped = word ? 1 : 0;
+    return 0;
 }
 
 int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
@@ -336,7 +433,7 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         if (rc) break;
         // the pollers' watchdog word (never set in correct operation) comes back with the results
         if (!s.err_word) CUDA_TRY(cudaHostAlloc(&s.err_word, sizeof(int), cudaHostAllocDefault));
-        CUDA_TRY(cudaMemcpyAsync(s.err_word, reinterpret_cast<int*>(dws + align_up(n * 4)) + kSyncError, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(s.err_word, ctx->err_word, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->popt + lo * P, dpopt, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->info + lo, dinfo, n * 4, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(cudaMemcpyAsync(d->nfev + lo, dnfev, n * 4, cudaMemcpyDeviceToHost, s.stream));
@@ -348,7 +445,10 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     for (auto& s : ctx->slots) {
         cudaError_t e = cudaStreamSynchronize(s.stream);
         if (e != cudaSuccess && rc == 0) rc = fail(std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
-        if (s.err_word && *s.err_word && rc == 0) rc = fail("a straggler poller kernel gave up waiting (watchdog); results are incomplete");
+        if (s.err_word && *s.err_word && rc == 0) {
+            rc = fail("a straggler poller kernel gave up waiting (watchdog); unfinished fits keep info = DPHLM_INFO_UNFINISHED");
+            cudaMemset(ctx->err_word, 0, sizeof(int));
+        }
         if (s.err_word) *s.err_word = 0;
     }
     cudaSetDevice(prev);
@@ -393,6 +493,33 @@ int dphlm_last_kernel_ms(float ms[3]) {
     CUDA_TRY(cudaEventElapsedTime(&ms[0], g_timing.ev[0], g_timing.ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&ms[1], g_timing.ev[1], g_timing.ev[2]));
     CUDA_TRY(cudaEventElapsedTime(&ms[2], g_timing.ev[2], g_timing.ev[3]));
+    return 0;
+}
+
+int dphlm_measure_fp32_peak(double* tflops) {
+    if (!tflops) return fail("null pointer");
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, threads = 256, iters = 8192;
+    float* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {  // the first repetitions also bring the clocks up
+        cudaEventRecord(e0);
+        dphlm_ffma_chain_kernel<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+        cudaEventRecord(e1);
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = 2.0 * 16 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
     return 0;
 }
 

@@ -77,6 +77,7 @@ struct KArgs {
     int budget;             // trips before parking; <= 0: never
     int max_backlog;        // parked fits waiting for a poller beyond which the main kernels stop parking
     int on_demand_tail;     // != 0: the last wave of fits is claimed on demand, not ahead (IoDevice::stage)
+    int skip_prefit;        // host-side only: DPHLM_FLAG_SKIP_PREFIT
     long long n_fits;
     int h, w;
     Options opt;
@@ -122,6 +123,7 @@ struct IoDevice {
     long long next = -1;   // index of the staged fit, -1: nothing staged yet
 
     __device__ int budget() const { return (RESUME || a.budget <= 0 || a.produce.cap <= 0) ? 0x7fffffff : a.budget; }
+    __device__ const float* consts() const { return a.consts; }
 
     // append a record to a queue: count, record, fence, ready flag (in this order)
     __device__ static bool publish(const ParkQueue& q, const float* r, int nrec, long long fit) {
@@ -427,12 +429,16 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
 #endif
 
 // ------------------------------------------------------------------------------------ covariance
-// Per-fit parameter covariance from the Jacobian at `popt` (second return value of curve_fit):
+// Per-fit parameter covariance from the Jacobian at a given point (second return value of curve_fit; the reference
+// evaluates it at the last ACCEPTED point of lm(), lm.py:468-473, 489 -- `x_acc` of dphlm_fit_batch):
 //   kind 0: pinv(J^T J) of the unweighted Jacobian, the reference's pcov (dphtools/utils/lm.py:672-677);
 //   kind 1: Poisson Cramer-Rao bound (J^T diag(1/f) J)^-1, the uncertainty an MLE user actually wants
 //           (precedent: notebooks/MLE_LevMarq_4Param_2013_11_12.m:145-168).
-// Eight lanes per fit, no shared memory; a rank-deficient matrix (the reference would drop singular values)
-// yields NaNs.
+// Off the hot path, so it is done in float64: model and Jacobian from Mo::eval64, J^T J summed over eight lanes per fit,
+// then a cyclic Jacobi eigen-decomposition V diag(l) V^T on one lane and pinv = V diag(1/l) V^T over the eigenvalues above
+// eps max(M, P) l_max.  The reference cuts the SINGULAR VALUES of J at eps max(M, P) s_max (lm.py:675); from J^T J only
+// eigenvalues down to ~1e-16 l_max exist, so an exactly rank-deficient Jacobian (a zero or repeated column) gives the
+// reference's answer, while directions with 3e-14 < s / s_max < 2e-7 -- kept upstream, numerically meaningless -- are dropped.
 struct CovArgs {
     const float* popt;
     const float* xaxis;
@@ -442,61 +448,106 @@ struct CovArgs {
     int h, w, kind;
 };
 
+template <int P>
+__device__ void sym_pinv64(double (&a)[P][P], double cut_rel, double (&out)[P][P]) {
+    double v[P][P];
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = 0; j < P; ++j) v[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            diag += a[i][i] * a[i][i];
+#pragma unroll
+            for (int j = i + 1; j < P; ++j) off += a[i][j] * a[i][j];
+        }
+        if (off <= 1e-60 || off <= 1e-34 * diag) break;
+#pragma unroll
+        for (int p = 0; p < P - 1; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < P; ++q) {
+                const double apq = a[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+                for (int k = 0; k < P; ++k) {  // columns p, q of A and V
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq;
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq;
+                }
+#pragma unroll
+                for (int k = 0; k < P; ++k) {  // rows p, q of A
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk;
+                }
+            }
+        }
+    }
+    double lmax = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) lmax = fmax(lmax, a[i][i]);
+    double inv[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) inv[i] = (a[i][i] > cut_rel * lmax && a[i][i] > 0.0) ? 1.0 / a[i][i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < P; ++k) s += v[i][k] * inv[k] * v[j][k];
+            out[i][j] = s;
+        }
+}
+
 template <class Mo>
 __global__ void __launch_bounds__(128) dphlm_cov_kernel(const CovArgs a) {
     constexpr int P = Mo::P, G = 8;
     const int lane = threadIdx.x & 31;
     const long long fit = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool active = fit < a.n_fits;
-    Lanes<G> ln{lane % G, 0xffu << ((lane / G) * G)};
-    float p[P];
+    const int gl = lane % G;
+    double p[P];
 #pragma unroll
-    for (int k = 0; k < P; ++k) p[k] = active ? a.popt[fit * P + k] : 1.0f;
-    typename Mo::Par q;
-    Mo::set_consts(q, a.consts);
-    Mo::prepare(p, q);
-    __shared__ __align__(16) float tables[(128 / G) * (Mo::kTable > 0 ? Mo::kTable : 4)];
-    {
-        float zero[P];
+    for (int k = 0; k < P; ++k) p[k] = active ? double(a.popt[fit * P + k]) : 1.0;
+    double A[P][P];
 #pragma unroll
-        for (int k = 0; k < P; ++k) zero[k] = 0.0f;
-        typename Mo::Step st;
-        Mo::prepare_step(q, q, zero, st);
-        const typename Mo::Par q0 = q;
-        Mo::fill_tables(ln, q0, q, st, tables + (threadIdx.x / G) * Mo::kTable, a.h, a.w, 2);  // first pass, buffer 0
-    }
-    Acc<P, float> acc;
-    acc.clear();
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = 0; j < P; ++j) A[i][j] = 0.0;
     const int M = a.h * a.w;
-    for (int i = ln.lane; i < M; i += G) {
-        typename Mo::template Geo<float> g;
-        float e[Mo::NE], J[P];
-        const float cx = a.xaxis ? a.xaxis[i] : float(i % a.w), cy = a.xaxis ? float(i) : float(i / a.w);
-        Mo::geometry(q, cx, cy, g);
-        Mo::expo(q, g, e);
-        Mo::jac(q, g, e, J);
-        float wgt = 1.0f;
-        if (a.kind == 1) {
-            const float f = Mo::value(q, e);
-            wgt = f > 0.0f ? f_rcp(f) : 0.0f;
+    for (int i = gl; i < M; i += G) {
+        double f, J[P];
+        const double cx = a.xaxis ? double(a.xaxis[i]) : double(i % a.w), cy = a.xaxis ? double(i) : double(i / a.w);
+        Mo::eval64(p, a.consts, cx, cy, f, J);
+        double wgt = 1.0;
+        if (a.kind == 1) wgt = f > 0.0 ? 1.0 / f : 0.0;
+#pragma unroll
+        for (int r = 0; r < P; ++r)
+#pragma unroll
+            for (int c = r; c < P; ++c) A[r][c] += wgt * J[r] * J[c];
+    }
+#pragma unroll
+    for (int r = 0; r < P; ++r)
+#pragma unroll
+        for (int c = r; c < P; ++c) {
+            double v = A[r][c];
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            A[r][c] = A[c][r] = v;
         }
-        acc.add(J, wgt, 0.0f);
-    }
-    ln.template sum_all<NT<P>::value>(acc.A);
-    if (!active || ln.lane != 0) return;
-    float U[NT<P>::value], zero[P], col[P];
+    if (!active || gl != 0) return;
+    double out[P][P];
+    sym_pinv64<P>(A, 2.220446049250313e-16 * double(M > P ? M : P), out);
 #pragma unroll
-    for (int k = 0; k < P; ++k) zero[k] = 0.0f;
-    const bool ok = chol_factor<P>(acc.A, zero, 0.0f, U);
+    for (int r = 0; r < P; ++r)
 #pragma unroll
-    for (int c = 0; c < P; ++c) {
-        float rhs[P];
-#pragma unroll
-        for (int k = 0; k < P; ++k) rhs[k] = k == c ? -1.0f : 0.0f;
-        chol_solve_neg<P>(U, rhs, col);
-#pragma unroll
-        for (int k = 0; k < P; ++k) a.pcov[(fit * P + k) * P + c] = ok ? col[k] : __int_as_float(0x7fc00000);
-    }
+        for (int c = 0; c < P; ++c) a.pcov[(fit * P + r) * P + c] = float(out[r][c]);
 }
 
 template <class Mo>
@@ -528,6 +579,17 @@ struct DeviceCtx {
         cudaEvent_t fork_ev = nullptr, mid_ev = nullptr, join_a = nullptr, join_b = nullptr;
     } sides[4];
     unsigned next_side = 0;
+    // pipelined calls (DPHLM_FLAG_PIPELINED): the library's own streams, used round-robin; `in_ev` orders a call behind the
+    // caller's stream, `done_ev` is what dphlm_join() makes the caller's stream wait for
+    static constexpr int kPipeMax = 4;
+    std::mutex pipe_mu;
+    struct Pipe {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t in_ev = nullptr, done_ev = nullptr;
+        bool pending = false;
+    } pipes[kPipeMax];
+    unsigned next_pipe = 0;
+    int* err_word = nullptr;  // device: raised by a straggler kernel that gave up waiting (sticky until dphlm_call_status)
 };
 
 template <class Kern>
@@ -535,8 +597,9 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
                  bool early_start = false) {
     KArgs a = a0;
     if (smem > 227 * 1024) return ::dphlm::fail("ROI too large for the shared-memory layout of this group size");
-    // attribute setup and occupancy query once per (kernel instantiation, device, shared-memory size)
-    struct Cached { size_t smem = 0; int occ = 0; };
+    // attribute setup once per (kernel instantiation, device) -- at the maximum, so that it never shrinks under a concurrent
+    // caller with a larger ROI -- and one occupancy query per shared-memory size
+    struct Cached { bool attr = false; std::map<size_t, int> occ; };
     static std::map<std::pair<const void*, int>, Cached> cache;  // Kern is one function-pointer type for all kernels
     static std::mutex cache_mu;
     int dev = 0;
@@ -545,16 +608,17 @@ int launch_stage(Kern kern, const KArgs& a0, int fpw, size_t smem, DeviceCtx* ct
     {
         std::lock_guard<std::mutex> lk(cache_mu);
         Cached& c = cache[std::make_pair(reinterpret_cast<const void*>(kern), dev)];
-        if (c.occ == 0 || c.smem != smem) {
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (!c.attr) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            int o = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kWarps * 32, smem));
-            if (o < 1) return ::dphlm::fail("kernel does not fit on an SM");
-            c.smem = smem;
-            c.occ = o;
+            c.attr = true;
         }
-        occ = c.occ;
+        int& o = c.occ[smem];
+        if (o == 0) {
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kWarps * 32, smem));
+            if (o < 1) { c.occ.erase(smem); return ::dphlm::fail("kernel does not fit on an SM"); }
+        }
+        occ = o;
     }
     // a.counter points into the call's own workspace header (zeroed once per call by fit_device)
     // main kernels fill the machine minus the CTA slots reserved for the concurrently running pollers
@@ -611,6 +675,7 @@ struct ParkLists {  // carved from the workspace by fit_device
 // "last CTA has exited" flag of the kernels that feed it, never the other way round.
 template <class Mo, bool MLE, int G>
 int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t stream) {
+    const bool skip_prefit = a0.skip_prefit != 0;  // lm() alone: p_ls aliases p0, every pre-fit exit code starts as 1
     const int M = a0.h * a0.w;
     constexpr int FPW = 32 / G;
     const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w)));
@@ -627,13 +692,14 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     a.produce = a.consume[0] = a.consume[1] = none;
     a.wait_done[0] = a.wait_done[1] = nullptr;
     a.exit_counter = a.done_flag = nullptr;
-    a.error_flag = pl.sync ? pl.sync + kSyncError : nullptr;
+    a.error_flag = ctx->err_word;
     KArgs b = a;
     b.counter = counters + 1;
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[0], stream));
     if (!handoff) {
         a.budget = b.budget = 0;
-        int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream);
+        int rc = 0;
+        if (!skip_prefit) rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream);
         if (rc) return rc;
         if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
         rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream);
@@ -653,13 +719,16 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     aw.wait_done[0] = pl.sync + kSyncDoneAMain;
     aw.exit_counter = pl.sync + kSyncExitAWide; aw.done_flag = pl.sync + kSyncDoneAWide;
     CUDA_TRY(cudaEventRecord(sd.fork_ev, stream));
-    CUDA_TRY(cudaStreamWaitEvent(sd.stream_a, sd.fork_ev, 0));
+    if (!skip_prefit) CUDA_TRY(cudaStreamWaitEvent(sd.stream_a, sd.fork_ev, 0));
     CUDA_TRY(cudaStreamWaitEvent(sd.stream_b, sd.fork_ev, 0));
-    int rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream, 2 * kPollerCtas);
-    if (rc) return rc;
-    rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, aw, 1, smem_w, ctx, sd.stream_a, 0, kPollerCtas);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(sd.join_a, sd.stream_a));
+    int rc = 0;
+    if (!skip_prefit) {
+        rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream, 2 * kPollerCtas);
+        if (rc) return rc;
+        rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, aw, 1, smem_w, ctx, sd.stream_a, 0, kPollerCtas);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(sd.join_a, sd.stream_a));
+    }
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[1], stream));
     // lm() main + its poller (both behind the pre-fit main kernel)
     b.budget = budget_from_env("DPHLM_BUDGET_B", kBudgetMain);
@@ -668,20 +737,20 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     KArgs bw = b;
     bw.budget = 0;
     bw.produce = none;
-    bw.consume[0] = pl.queue(1); bw.consume[1] = pl.queue(2);
-    bw.wait_done[0] = pl.sync + kSyncDoneBMain; bw.wait_done[1] = pl.sync + kSyncDoneAWide;
+    bw.consume[0] = pl.queue(1); bw.consume[1] = skip_prefit ? none : pl.queue(2);
+    bw.wait_done[0] = pl.sync + kSyncDoneBMain; bw.wait_done[1] = skip_prefit ? nullptr : pl.sync + kSyncDoneAWide;
     bw.exit_counter = bw.done_flag = nullptr;
     // The lm() kernel directly follows the pre-fit kernel in the stream and may start in the CTA slots that one frees while its
     // last fits finish: it waits per fit for the pre-fit's exit code (IoDevice::fetch), not for the grid.  Timing events
     // between the two launches would serialise them, so a timed call keeps the plain stream order.
-    const bool early = !a.ev && !getenv("DPHLM_NO_EARLY_START");
+    const bool early = !a.ev && !skip_prefit && !getenv("DPHLM_NO_EARLY_START");
     rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream, 2 * kPollerCtas, 0, early);
     if (rc) return rc;
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));  // end of the lm() main kernel itself
     rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, bw, 1, smem_w, ctx, sd.stream_b, 0, kPollerCtas);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(sd.join_b, sd.stream_b));
-    CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_a, 0));
+    if (!skip_prefit) CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_a, 0));
     CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_b, 0));
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[3], stream));  // the pollers have finished the stragglers
     return 0;

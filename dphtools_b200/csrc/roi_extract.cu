@@ -85,6 +85,8 @@ extern "C" int dphlm_extract_rois(const dphlm_extract_desc* d, void* stream) {
     if (d->n_peaks < 0 || d->n_frames < 1 || d->height < 1 || d->width < 1) return fail("bad frame stack shape");
     if (d->roi < 1 || d->roi > 31) return fail("roi must be 1..31 pixels");
     if (d->roi > d->height || d->roi > d->width) return fail("roi larger than the frame");
+    // the parabola vertex is derived for abscissae symmetric about the window centre (localize_peak asserts odd shapes too)
+    if (d->refine && d->roi % 2 == 0) return fail("refine needs an odd roi");
     if (d->frame_dtype != DPHLM_F32 && d->frame_dtype != DPHLM_U16) return fail("frame_dtype must be DPHLM_F32 or DPHLM_U16");
     if (d->n_peaks == 0) return 0;
     if (!d->frames || !d->peaks || !d->rois || !d->p0) return fail("null frames/peaks/rois/p0 pointer");

@@ -11,12 +11,15 @@ turns them back into the reference's exceptions.
 """
 
 import ctypes
+import logging
 import threading
 from collections import namedtuple
 
 import numpy as np
 
 from . import _lib, models
+
+logger = logging.getLogger(__name__)  # the reference logs through a module logger too (lm.py:27)
 
 FTOL = XTOL = 1.49012e-8
 
@@ -95,7 +98,7 @@ def _check(rc):
 
 def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
                     factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None, timing=False, out=None,
-                    return_pcov=None, return_x_acc=False):
+                    return_pcov=None, return_x_acc=False, pipelined=False, skip_prefit=False):
     """Fit ``N`` independent ROIs / histograms: the batched form of per-ROI
     ``curve_fit(model, xdata, roi.ravel(), p0, jac=model.jac, method=method)`` (``lm.py:510-685``).
 
@@ -111,7 +114,13 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     timing : device path only: record CUDA events around the two kernels (``_lib.last_kernel_ms()``).
     return_x_acc : also return the last ACCEPTED point of ``lm()`` (``[N, P]``): the reference evaluates ``infodict['fjac']``
         and ``pcov`` there, one converged step before ``popt`` (``lm.py:468-473, 489``).
-    return_pcov : ``"jtj"`` or ``"crlb"``: also return the ``[N, P, P]`` covariances (see :func:`covariance`).
+    return_pcov : ``"jtj"`` or ``"crlb"``: also return the ``[N, P, P]`` covariances (see :func:`covariance`).  ``"jtj"`` is the
+        reference's ``pcov``: evaluated at the last accepted point (``x_acc``) with its singular-value cut-off.
+    pipelined : device path only: enqueue the call on one of the library's own streams and do NOT make the current stream
+        wait for it (``DPHLM_FLAG_PIPELINED``): consecutive calls overlap, the drain and the stragglers of one run under the
+        next.  The results are pending until :func:`join` has been called; the inputs are kept alive until then.
+    skip_prefit : start the ``lm()`` loop directly at ``p0`` (``DPHLM_FLAG_SKIP_PREFIT``): the reference's ``lm()`` rather
+        than its ``curve_fit`` (``lm.py:221-236``).
     out : host path only: a ``BatchResult`` of preallocated C-contiguous arrays to write into (use
         :func:`pinned_empty` buffers, for the inputs too, so that the copies run asynchronously).
     device : host path only: CUDA device index, or a list of indices to shard the batch over several
@@ -124,11 +133,17 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     model = _resolve_model(model)
     one_d = model.model_id in models.ONE_D
     if _is_torch(data) and data.is_cuda:
+        want_acc = return_x_acc or return_pcov == "jtj"
         res = _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
-                          return_counts, group_lanes, timing, return_x_acc)
+                          return_counts, group_lanes, timing, want_acc, pipelined, skip_prefit)
         if return_pcov:
-            res = res._replace(pcov=covariance(model, res.popt, data.shape[1:], return_pcov, xdata))
+            if pipelined:
+                raise ValueError("return_pcov needs the results: call covariance() after join()")
+            at = res.x_acc if return_pcov == "jtj" else res.popt
+            res = res._replace(pcov=covariance(model, at, data.shape[1:], return_pcov, xdata))
         return res
+    if pipelined:
+        raise ValueError("pipelined=True needs CUDA tensors (the host entry point overlaps its own chunks)")
     if _is_torch(data):
         data = data.numpy()
     if _is_torch(p0):
@@ -152,13 +167,13 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         out = BatchResult(
             np.empty((n, n_param), np.float32), np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32),
             np.empty((n, n_param), np.float32) if return_stage1 else None, np.empty((n, 4), np.int32) if return_counts else None, None,
-            np.empty((n, n_param), np.float32) if return_x_acc else None,
+            np.empty((n, n_param), np.float32) if (return_x_acc or return_pcov == "jtj") else None,
         )
     else:
         want = [((n, n_param), np.float32), ((n,), np.int32), ((n,), np.int32), ((n,), np.float32),
                 ((n, n_param), np.float32) if return_stage1 else None, ((n, 4), np.int32) if return_counts else None]
         out = BatchResult(*(tuple(out) + (None,) * (8 - len(out))))
-        if return_x_acc and out.x_acc is None:
+        if (return_x_acc or return_pcov == "jtj") and out.x_acc is None:
             out = out._replace(x_acc=np.empty((n, n_param), np.float32))
         for a, w in zip(out, want):
             if w is not None and (a is None or a.shape != w[0] or a.dtype != w[1] or not a.flags.c_contiguous):
@@ -175,8 +190,8 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         d.popt, d.info, d.nfev, d.chisq = (a[lo:hi].ctypes.data for a in tuple(out)[:4])
         d.p_ls = out.p_ls[lo:hi].ctypes.data if return_stage1 else None
         d.counts = out.counts[lo:hi].ctypes.data if return_counts else None
-        d.x_acc = out.x_acc[lo:hi].ctypes.data if return_x_acc else None
-        d.flags = _lib.FLAG_DATA_U16 if u16 else 0
+        d.x_acc = out.x_acc[lo:hi].ctypes.data if out.x_acc is not None else None
+        d.flags = (_lib.FLAG_DATA_U16 if u16 else 0) | (_lib.FLAG_SKIP_PREFIT if skip_prefit else 0)
         return _lib.lib().dphlm_fit_batch_host(ctypes.byref(d), dev)
 
     if len(devices) == 1:
@@ -198,8 +213,36 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         if errs:
             raise RuntimeError("dphlm: " + errs[0])
     if return_pcov:
-        out = out._replace(pcov=covariance(model, out.popt, data.shape[1:], return_pcov, xa))
+        at = out.x_acc if return_pcov == "jtj" else out.popt
+        out = out._replace(pcov=covariance(model, at, data.shape[1:], return_pcov, xa))
     return out
+
+
+_pending = {}  # device index -> buffers of pipelined calls that must stay alive until join()
+
+
+def join(device=None):
+    """Make the current stream of ``device`` (default: the current device) wait for every pending ``pipelined=True`` call
+    (``dphlm_join``).  Asynchronous; afterwards the results may be used on that stream like any other tensor."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    with torch.cuda.device(dev):
+        _check(_lib.lib().dphlm_join(ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    _pending.pop(dev.index, None)
+
+
+def call_status(device=None):
+    """True if a straggler kernel of ``device`` gave up waiting since the last call of this function (``dphlm_call_status``;
+    never in correct operation).  Synchronises the device.  Fits that were dropped keep ``info == INFO_UNFINISHED``."""
+    import torch
+
+    word = ctypes.c_int(0)
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        _check(_lib.lib().dphlm_call_status(ctypes.byref(word)))
+    if word.value:
+        logger.warning("dphlm: a straggler kernel gave up waiting; unfinished fits keep info = INFO_UNFINISHED")
+    return bool(word.value)
 
 
 class _PinnedBlock:
@@ -228,7 +271,7 @@ def pinned_empty(shape, dtype=np.float32):
 
 
 def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1, return_counts, group_lanes,
-                timing=False, return_x_acc=False):
+                timing=False, return_x_acc=False, pipelined=False, skip_prefit=False):
     import torch
 
     if data.dtype != torch.float32 or not data.is_contiguous():
@@ -262,11 +305,14 @@ def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev,
     d.p_ls = p_ls.data_ptr() if return_stage1 else None
     d.counts = counts.data_ptr() if return_counts else None
     d.x_acc = x_acc.data_ptr() if return_x_acc else None
-    d.flags = _lib.FLAG_TIMING if timing else 0
+    d.flags = (_lib.FLAG_TIMING if timing else 0) | (_lib.FLAG_PIPELINED if pipelined else 0) | (_lib.FLAG_SKIP_PREFIT if skip_prefit else 0)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _check(_lib.lib().dphlm_fit_batch(ctypes.byref(d), ctypes.c_void_p(stream)))
-    return BatchResult(popt, info, nfev, chisq, p_ls, counts, None, x_acc)
+    res = BatchResult(popt, info, nfev, chisq, p_ls, counts, None, x_acc)
+    if pipelined:  # the kernels run on the library's streams: nothing they touch may go back to torch's allocator before join()
+        _pending.setdefault(dev.index, []).append((data, p0, xa, consts, res))
+    return res
 
 
 def covariance(model, popt, shape, kind="jtj", xdata=None):
@@ -318,14 +364,16 @@ def extract_rois(frames, peaks, roi=11, sigma0=1.3, refine=False):
     import torch
 
     fr = torch.as_tensor(frames)
-    if fr.dtype in (torch.uint16, torch.int16):
-        fr, code = fr.view(torch.int16) if fr.dtype == torch.uint16 else fr, 1
+    if fr.dtype == torch.uint16:
+        fr, code = fr.view(torch.int16), 1  # raw camera counts: the kernel reads them as unsigned short
     else:
-        fr, code = fr.float(), 0
+        fr, code = fr.float(), 0  # includes int16 (background-subtracted, signed) frames
     fr = fr.cuda().contiguous()
     pk = torch.as_tensor(peaks, dtype=torch.int32).to(fr.device).contiguous()
     if fr.dim() != 3 or pk.dim() != 2 or pk.shape[1] != 3:
         raise ValueError("frames must be [F,H,W] and peaks [N,3] (frame, row, column)")
+    if refine and roi % 2 == 0:
+        raise ValueError("refine needs an odd roi (the parabola vertex assumes a window symmetric about its centre)")
     n = pk.shape[0]
     rois = torch.empty((n, roi, roi), dtype=torch.float32, device=fr.device)
     p0 = torch.empty((n, 5), dtype=torch.float32, device=fr.device)
@@ -379,6 +427,8 @@ def curve_fit(f, xdata, ydata, p0=None, sigma=None, absolute_sigma=False, check_
     if jac is None:
         raise NotImplementedError("You need a Jacobian")
     model = _resolve_model(f)
+    if jac is not model.jac:
+        raise NotImplementedError("method='ls'|'mle' uses the analytic Jacobian built into the kernels: pass jac=%s.jac" % model.model_name)
     unknown = set(kwargs) - {"ftol", "xtol", "gtol", "maxfev", "factor", "epsfcn", "diag", "col_deriv"}
     if unknown:
         raise TypeError("unexpected keyword arguments %s" % sorted(unknown))
@@ -404,6 +454,7 @@ def curve_fit(f, xdata, ydata, p0=None, sigma=None, absolute_sigma=False, check_
     res = curve_fit_batch(model, data, p0[None], method, xa, ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev,
                           factor=kwargs.get("factor", 100.0), return_x_acc=True)
     info, popt = int(res.info[0]), res.popt[0].astype(float)
+    logger.debug("curve_fit(method=%r): info %d after %d lm() evaluations", method, info, int(res.nfev[0]) + 1)
     fmt = dict(ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev)
     if info == -100:
         raise ValueError("array must not contain infs or NaNs")
@@ -424,3 +475,63 @@ def curve_fit(f, xdata, ydata, p0=None, sigma=None, absolute_sigma=False, check_
         fvec = np.where(fvec <= 0, 0.0, fvec) if method == "mle" else fvec - ydata
         return popt, pcov, dict(fvec=fvec, fjac=fjac, nfev=int(res.nfev[0]), chisq=float(res.chisq[0])), errmsg, info
     return popt, pcov
+
+
+def _fit_arrays(model, xdata, ydata, x0, what):
+    """(data [1, ...], shared x axis or None) of one fit for :func:`curve_fit_batch`."""
+    if model.model_id in models.ONE_D:
+        return ydata.reshape(1, -1), xdata.ravel()
+    shape = _grid_shape(xdata)
+    if shape is None or shape[0] * shape[1] != ydata.size:
+        raise NotImplementedError("2-D models need xdata = models.roi_grid(h, w), the pixel grid of a row-major ROI (%s)" % what)
+    return ydata.reshape((1,) + shape), None
+
+
+def lm(func, x0, args=(), Dfun=None, full_output=False, col_deriv=True, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
+       epsfcn=None, factor=100, diag=None, method="ls"):
+    """Counterpart of ``dphtools.utils.lm.lm`` (``lm.py:221-507``): the damped normal-equation loop ALONE, from ``x0``,
+    without the least-squares pre-fit that ``curve_fit`` puts in front of it (``DPHLM_FLAG_SKIP_PREFIT``).
+
+    Upstream ``func`` is a closure over the data -- ``func(params)`` returns the residuals (``'ls'``) or the pair
+    ``(model, data)`` (``'mle'``, ``lm.py:121-146``) -- which a GPU kernel cannot look into.  Here ``func`` is a built-in
+    model of :mod:`dphtools_b200.models`, ``Dfun`` its ``.jac`` and ``args = (xdata, ydata)``; everything else (keywords,
+    guards in upstream order, return values, ``infodict`` keys, warnings and exceptions for ``info`` outside 1..4 when
+    ``full_output`` is false, ``lm.py:491-507``) is as upstream.
+    """
+    x0 = np.asarray(x0, dtype=float).flatten()
+    if not isinstance(args, tuple):
+        args = (args,)
+    if Dfun is None:
+        raise NotImplementedError
+    if not col_deriv:
+        raise NotImplementedError("Column derivatives required")
+    if maxfev is None:
+        maxfev = 100 * (len(x0) + 1)
+    if method not in ("ls", "mle"):
+        raise TypeError("Method {} not recognized".format(method))
+    model = _resolve_model(func)
+    if Dfun is not model.jac:
+        raise NotImplementedError("lm() uses the analytic Jacobian built into the kernels: pass Dfun=%s.jac" % model.model_name)
+    if len(args) != 2:
+        raise TypeError("lm() of dphtools_b200 takes args=(xdata, ydata)")
+    xdata, ydata = np.asarray(args[0], dtype=float), np.asarray(args[1], dtype=float)
+    data, xa = _fit_arrays(model, xdata, ydata, x0, "args[0]")
+    res = curve_fit_batch(model, data, x0[None], method, xa, ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev, factor=float(factor),
+                          return_x_acc=True, skip_prefit=True)
+    info, popt = int(res.info[0]), res.popt[0].astype(float)
+    fmt = dict(ftol=ftol, xtol=xtol, gtol=gtol, maxfev=maxfev)
+    errmsg = _MESSAGES.get(info, "Unknown error.")
+    errmsg = errmsg.format(**fmt) if info in _MESSAGES else errmsg
+    logger.debug("Ended with %d function evaluations", int(res.nfev[0]) + 1)
+    if info not in (1, 2, 3, 4) and not full_output:
+        if info in (5, 6, 7, 8):
+            logger.warning(errmsg)  # lm.py:491-493
+        else:
+            raise TypeError(errmsg)  # lm.py:494-498 (errors["unknown"])
+    logger.debug(errmsg)
+    if not full_output:
+        return popt, None
+    fvec = model(xdata, *popt)
+    fvec = np.where(fvec <= 0, 0.0, fvec) if method == "mle" else fvec - ydata
+    fjac = model.jac(xdata, *res.x_acc[0].astype(float))  # J at the last accepted point (lm.py:468-473, 489)
+    return popt, None, dict(fvec=fvec, fjac=fjac, nfev=int(res.nfev[0])), errmsg, info

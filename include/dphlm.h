@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define DPHLM_VERSION 102
+#define DPHLM_VERSION 200
 
 /* model ids: callables a caller would pass as `f` to curve_fit (dphtools/utils/lm.py:510-512).
  * MULTI_EXP is the reference's own model (dphtools/utils/fitfuncs.py:20-52); the Gaussians are new:
@@ -44,7 +44,11 @@ enum dphlm_method { DPHLM_LS = 0, DPHLM_MLE = 1 };
  *   -k         the least-squares pre-fit (scipy curve_fit -> MINPACK lmder, lm.py:642-644) ended with
  *              ier = k not in 1..4 (k = 5: maxfev); scipy raises RuntimeError there
  *   -9         non-finite model value at p0
- *   -100       non-finite input data; the reference raises ValueError (lm.py:651-662)            */
+ *   -100       non-finite input data; the reference raises ValueError (lm.py:651-662)
+ *   DPHLM_INFO_UNFINISHED   the fit was never finished: every call pre-fills `info` with this value, so a fit dropped by a
+ *              failed launch or by a straggler kernel that gave up waiting (see dphlm_call_status) cannot be mistaken
+ *              for a result                                                                         */
+#define DPHLM_INFO_UNFINISHED (-2139062144) /* 0x80808080 */
 
 typedef struct dphlm_desc {
     int32_t model;       /* enum dphlm_model */
@@ -78,6 +82,15 @@ typedef struct dphlm_desc {
 /* flags: `data` points to uint16 camera counts instead of float32 (half the PCIe traffic on the host entry); they are
  * widened on the device before the fit */
 #define DPHLM_FLAG_DATA_U16 4
+/* flags (dphlm_fit_batch only): pipelined call.  The kernels are enqueued on one of the library's own streams behind everything
+ * that is in `stream` at the time of the call, and `stream` does NOT wait for them: consecutive pipelined calls overlap
+ * (two in flight; the tail of one call -- its last fits, its stragglers -- runs under the next call's kernels), which is
+ * worth ~25 % at 1e5 fits per call.  The caller must treat the outputs as pending, keep all buffers alive, and not feed
+ * them to later work until dphlm_join(stream) has made `stream` wait for every pending pipelined call. */
+#define DPHLM_FLAG_PIPELINED 8
+/* flags: skip the least-squares pre-fit: `p0` is the start of the lm() loop itself.  This is the reference's second public
+ * function, lm(func, x0, ..., method=) (dphtools/utils/lm.py:221-236), as opposed to curve_fit (lm.py:510-685). */
+#define DPHLM_FLAG_SKIP_PREFIT 16
 
 /* Fill the tolerances with the reference defaults (ftol = xtol = 1.49012e-8, gtol = 0, factor = 100,
  * maxfev = 0 -> 100 (P + 1); dphtools/utils/lm.py:228-233) and zero everything else. */
@@ -87,6 +100,15 @@ void dphlm_desc_init(dphlm_desc* d);
  * (dphtools/utils/lm.py:510-685).  All pointers are DEVICE pointers on the current device; the work is
  * enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call returns without waiting. */
 int dphlm_fit_batch(const dphlm_desc* d, void* stream);
+
+/* Makes `stream` wait for all pending DPHLM_FLAG_PIPELINED calls of the current device (asynchronous: enqueues event waits). */
+int dphlm_join(void* stream);
+
+/* Watchdog of the current device: the straggler kernels wait for work from the main kernels and give up after ~60 s without
+ * news (never in correct operation; reachable under a debugger or on a GPU shared with a long-running foreign kernel).
+ * Synchronises the device, writes 1 to *tripped if that has happened since the last call of this function, else 0, and
+ * clears the record.  Fits that were dropped keep info = DPHLM_INFO_UNFINISHED.  (dphlm_fit_batch_host checks by itself.) */
+int dphlm_call_status(int* tripped);
 
 /* Same contract with HOST pointers: copies the inputs to `device`, fits, copies the results back and
  * returns when they are in place.  Large batches are cut into chunks whose copies overlap the kernels. */
@@ -131,6 +153,10 @@ void dphlm_host_free(void* p);
  * kernels have finished the last straggler (the pollers run concurrently with the main kernels; a pre-fit that needs
  * hundreds of evaluations ends here).  Waits for that call to finish. */
 int dphlm_last_kernel_ms(float ms[3]);
+
+/* Measured FP32 throughput of the current device in TFLOP/s (independent FFMA chains, best of a few launches, ~10 ms):
+ * the denominator bench.py reports beside the nominal SMs x 128 x 2 x clock. */
+int dphlm_measure_fp32_peak(double* tflops);
 
 int dphlm_device_count(void);
 int dphlm_version(void);

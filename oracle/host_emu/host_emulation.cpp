@@ -26,6 +26,7 @@ struct Buffers {
     std::vector<Parked> parked;
     std::vector<char> was_parked;
     const float* consts;  // model constants of the call, or null
+    int skip_prefit = 0;  // lm() alone: stage B starts at p0 (DPHLM_FLAG_SKIP_PREFIT)
 };
 
 template <class Mo>
@@ -34,6 +35,7 @@ struct HostIoPrefit {
     long next = 0;
     size_t resumed = 0;
     int budget() const { return b.budget > 0 ? b.budget : 1 << 30; }
+    const float* consts() const { return b.consts; }
     bool park(const Lanes<1>&, const StageA<Mo>& st, long long fit) {
         if (b.was_parked[fit]) return false;  // park once
         b.was_parked[fit] = 1;
@@ -76,6 +78,7 @@ struct HostIoMain {
     long next = 0;
     size_t resumed = 0;
     int budget() const { return b.budget > 0 ? b.budget : 1 << 30; }
+    const float* consts() const { return b.consts; }
     bool park(const Lanes<1>&, const StageB<Mo, MLE>& st, long long fit) {
         if (b.was_parked[fit]) return false;
         b.was_parked[fit] = 1;
@@ -136,8 +139,16 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
     std::vector<double> table(Mo::table_floats(h, w) / 2 + 2);  // double: 16-byte aligned by operator new
     px.tbl = reinterpret_cast<float*>(table.data());
     px.w = w;
-    HostIoPrefit<Mo> ioa{b};
-    run_stage<StageA<Mo>, Mo, 1>(ln, px, opt, ioa);
+    if (b.skip_prefit) {
+        for (long i = 0; i < b.n; ++i) {
+            b.ier[i] = 1;
+            b.counts[4 * i] = 0;
+            for (int k = 0; k < Mo::P; ++k) b.p_ls[i * Mo::P + k] = b.p0[i * Mo::P + k];
+        }
+    } else {
+        HostIoPrefit<Mo> ioa{b};
+        run_stage<StageA<Mo>, Mo, 1>(ln, px, opt, ioa);
+    }
     b.parked.clear();
     b.was_parked.assign(b.n, 0);
     HostIoMain<Mo, MLE> iob{b};
@@ -147,9 +158,9 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
 extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, long n, const float* data,
                              const float* xaxis, const float* p0, float ftol, float xtol, float gtol, float factor,
                              int maxfev, int budget, float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts,
-                             const float* consts) {
+                             const float* consts, int skip_prefit) {
     Options opt{ftol, xtol, gtol, factor, maxfev};
-    Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0), budget, {}, std::vector<char>(n, 0), consts};
+    Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0), budget, {}, std::vector<char>(n, 0), consts, skip_prefit};
 #define RUN(...)                                                 \
     do {                                                         \
         if (method) run<__VA_ARGS__, true>(h, w, xaxis, opt, b);  \

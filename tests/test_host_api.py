@@ -15,12 +15,12 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(REPO, "include", "dphlm.h")).read()
-    declared = set(re.findall(r"\b(dphlm_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(dphlm_[a-z_0-9]+)\s*\(", header))
     assert declared == set(_lib.SYMBOLS)
     lib = _lib.lib()
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.dphlm_version() == 102
+    assert lib.dphlm_version() == 200
 
 
 def test_desc_layout_and_defaults():
