@@ -26,6 +26,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define DPH_HD __host__ __device__ __forceinline__
@@ -897,6 +898,23 @@ struct PixelState {
     DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * stride; }
 };
 
+#if defined(__CUDA_ARCH__)
+DPH_HD int float_as_int(float f) { return __float_as_int(f); }
+DPH_HD float int_as_float(int i) { return __int_as_float(i); }
+#else
+DPH_HD int float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+DPH_HD float int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+#endif
+
+// Entry k of the coordinate tables shared by all fits of a CTA: the pixel's coordinates (cy = bin index for 1-D data).
+template <class Mo>
+DPH_HD void fill_coords(float* cx, float* cy, int k, int h, int w, const float* xaxis) {
+    const int M = h * w, i = k < M ? k : M - 1;
+    (void)h;
+    cx[k] = xaxis ? xaxis[i] : float(i % w);
+    cy[k] = xaxis ? float(i) : float(i / w);
+}
+
 // Group of G lanes.  On the host G == 1 and the reductions are the identity.
 template <int G>
 struct Lanes {
@@ -1018,12 +1036,10 @@ DPH_HD void mle_weights(float f, float y, float& w, float& res) {
 // predicted model is f(x_new) + J(x_old) d.
 template <class Mo, bool MLE, bool PRED, class T>
 DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1, const typename Mo::Step& st, bool init,
-                          bool want_chi, T cx, T cy, T y, const T* e0in, T* e1, Acc<Mo::P, T>& n) {
+                          bool want_chi, const typename Mo::template Geo<T>& g1, T y, const T* e0in, T* e1, Acc<Mo::P, T>& n) {
     constexpr int P = Mo::P, NE = Mo::NE;
-    typename Mo::template Geo<T> g1;
     typename Mo::template Diff<T> df;
     T e0[NE], J[P];
-    Mo::geometry(q1, cx, cy, g1);
     Mo::expo(q1, g1, e1);
     if constexpr (Mo::kStoreE) {
 #pragma unroll
@@ -1099,6 +1115,7 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
     if (FAST) {
         Acc<P, f2> a2;
         a2.clear();
+        Acc<P, float> a1;
         const int npair = px.M >> 1;
 #if defined(__CUDA_ARCH__)
 #pragma unroll kPairUnroll
@@ -1113,13 +1130,14 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
             const f2 cx = *reinterpret_cast<const f2*>(px.cx + i);
             const f2 cy = *reinterpret_cast<const f2*>(px.cy + i);
             const f2 y = *reinterpret_cast<const f2*>(px.y + i);
-            pixel_regular<Mo, MLE, PRED, f2>(q0, q1, st, init, want_chi, cx, cy, y, e0, e1, a2);
+            typename Mo::template Geo<f2> g1;
+            Mo::geometry(q1, cx, cy, g1);
+            pixel_regular<Mo, MLE, PRED, f2>(q0, q1, st, init, want_chi, g1, y, e0, e1, a2);
             if constexpr (Mo::kStoreE) {
 #pragma unroll
                 for (int j = 0; j < NE; ++j) *reinterpret_cast<f2*>(e1b + j * stride + i) = e1[j];
             }
         }
-        Acc<P, float> a1;
 #pragma unroll
         for (int k = 0; k < NT<P>::value; ++k) a1.A[k] = v_hsum(a2.A[k]);
 #pragma unroll
@@ -1133,7 +1151,9 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
 #pragma unroll
                 for (int j = 0; j < NE; ++j) e0[j] = e0b[j * stride + i];
             }
-            pixel_regular<Mo, MLE, PRED, float>(q0, q1, st, init, want_chi, px.cx[i], px.cy[i], px.y[i], e0, e1, a1);
+            typename Mo::template Geo<float> g1;
+            Mo::geometry(q1, px.cx[i], px.cy[i], g1);
+            pixel_regular<Mo, MLE, PRED, float>(q0, q1, st, init, want_chi, g1, px.y[i], e0, e1, a1);
             if constexpr (Mo::kStoreE) {
 #pragma unroll
                 for (int j = 0; j < NE; ++j) e1b[j * stride + i] = e1[j];

@@ -348,7 +348,7 @@ int dphlm_call_status(int* tripped) {
     return 0;
 }
 
-int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
+static int host_enqueue(const dphlm_desc* d, int device) {
     if (validate(d)) return -1;
     if (d->n_fits == 0) return 0;
     int prev = 0;
@@ -442,7 +442,19 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
         if (d->counts) CUDA_TRY(cudaMemcpyAsync(d->counts + lo * 4, dcnt, n * 16, cudaMemcpyDeviceToHost, s.stream));
         if (d->x_acc) CUDA_TRY(cudaMemcpyAsync(d->x_acc + lo * P, dxacc, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
     }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+static int host_wait(int device) {
+    if (device < 0 || device >= 64) return fail("device index out of range");
+    int prev = 0, rc = 0;
+    CUDA_TRY(cudaGetDevice(&prev));
+    CUDA_TRY(cudaSetDevice(device));
+    DeviceCtx* ctx;
+    if (get_ctx(device, &ctx)) return -1;
     for (auto& s : ctx->slots) {
+        if (!s.stream) continue;
         cudaError_t e = cudaStreamSynchronize(s.stream);
         if (e != cudaSuccess && rc == 0) rc = fail(std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
         if (s.err_word && *s.err_word && rc == 0) {
@@ -454,6 +466,16 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
     cudaSetDevice(prev);
     return rc;
 }
+
+int dphlm_fit_batch_host(const dphlm_desc* d, int device) {
+    const int rc = host_enqueue(d, device);
+    const int rw = host_wait(device);  // also after a failed enqueue: nothing of this call may still be in flight on return
+    return rc ? rc : rw;
+}
+
+int dphlm_fit_batch_host_async(const dphlm_desc* d, int device) { return host_enqueue(d, device); }
+
+int dphlm_host_wait(int device) { return host_wait(device); }
 
 int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int kind, void* stream) {
     if (validate_shape(d)) return -1;

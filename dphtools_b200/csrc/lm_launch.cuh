@@ -398,11 +398,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
     const int Mp = (M + 1) & ~1;
     float* cx = smem;
     float* cy = smem + Mp;
-    for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
-        const int k = i < M ? i : M - 1;
-        cx[i] = a.xaxis ? a.xaxis[k] : float(k % a.w);
-        cy[i] = a.xaxis ? float(k) : float(k / a.w);  // 1-D data: the bin index
-    }
+    for (int i = threadIdx.x; i < Mp; i += blockDim.x) fill_coords<Mo>(cx, cy, i, a.h, a.w, a.xaxis);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G;

@@ -98,7 +98,7 @@ def _check(rc):
 
 def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
                     factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None, timing=False, out=None,
-                    return_pcov=None, return_x_acc=False, pipelined=False, skip_prefit=False):
+                    return_pcov=None, return_x_acc=False, pipelined=False, skip_prefit=False, wait=True):
     """Fit ``N`` independent ROIs / histograms: the batched form of per-ROI
     ``curve_fit(model, xdata, roi.ravel(), p0, jac=model.jac, method=method)`` (``lm.py:510-685``).
 
@@ -119,6 +119,9 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     pipelined : device path only: enqueue the call on one of the library's own streams and do NOT make the current stream
         wait for it (``DPHLM_FLAG_PIPELINED``): consecutive calls overlap, the drain and the stragglers of one run under the
         next.  The results are pending until :func:`join` has been called; the inputs are kept alive until then.
+    wait : host path only: ``False`` returns as soon as the copies and kernels are enqueued (``dphlm_fit_batch_host_async``; use
+        :func:`pinned_empty` buffers and leave them alone until :func:`host_wait`), so that the next batch's upload overlaps
+        this batch's kernels.
     skip_prefit : start the ``lm()`` loop directly at ``p0`` (``DPHLM_FLAG_SKIP_PREFIT``): the reference's ``lm()`` rather
         than its ``curve_fit`` (``lm.py:221-236``).
     out : host path only: a ``BatchResult`` of preallocated C-contiguous arrays to write into (use
@@ -143,7 +146,9 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
             res = res._replace(pcov=covariance(model, at, data.shape[1:], return_pcov, xdata))
         return res
     if pipelined:
-        raise ValueError("pipelined=True needs CUDA tensors (the host entry point overlaps its own chunks)")
+        raise ValueError("pipelined=True needs CUDA tensors (the host entry point overlaps its own chunks; see wait=False)")
+    if return_pcov and not wait:
+        raise ValueError("return_pcov needs the results: call covariance() after host_wait()")
     if _is_torch(data):
         data = data.numpy()
     if _is_torch(p0):
@@ -192,6 +197,9 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         d.counts = out.counts[lo:hi].ctypes.data if return_counts else None
         d.x_acc = out.x_acc[lo:hi].ctypes.data if out.x_acc is not None else None
         d.flags = (_lib.FLAG_DATA_U16 if u16 else 0) | (_lib.FLAG_SKIP_PREFIT if skip_prefit else 0)
+        if not wait:
+            _host_pending.setdefault(dev, []).append((data, p0, xa, consts, out))  # keep the buffers alive until host_wait()
+            return _lib.lib().dphlm_fit_batch_host_async(ctypes.byref(d), dev)
         return _lib.lib().dphlm_fit_batch_host(ctypes.byref(d), dev)
 
     if len(devices) == 1:
@@ -216,6 +224,17 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         at = out.x_acc if return_pcov == "jtj" else out.popt
         out = out._replace(pcov=covariance(model, at, data.shape[1:], return_pcov, xa))
     return out
+
+
+_host_pending = {}
+
+
+def host_wait(device=0):
+    """Wait for every ``wait=False`` host call of ``device`` (an index or a list of indices) and raise their errors."""
+    for dev in ([device] if isinstance(device, int) else list(device)):
+        rc = _lib.lib().dphlm_host_wait(dev)
+        _host_pending.pop(dev, None)
+        _check(rc)
 
 
 _pending = {}  # device index -> buffers of pipelined calls that must stay alive until join()

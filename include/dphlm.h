@@ -114,6 +114,13 @@ int dphlm_call_status(int* tripped);
  * returns when they are in place.  Large batches are cut into chunks whose copies overlap the kernels. */
 int dphlm_fit_batch_host(const dphlm_desc* d, int device);
 
+/* The same without the final wait: returns once the copies and kernels of the call are enqueued (from page-locked buffers
+ * nothing blocks), so that the caller can prepare and enqueue the next batch -- whose host-to-device copies then overlap
+ * this batch's kernels and result copies.  The buffers must stay untouched until dphlm_host_wait(device), which waits for
+ * every enqueued call of the device and reports their errors. */
+int dphlm_fit_batch_host_async(const dphlm_desc* d, int device);
+int dphlm_host_wait(int device);
+
 /* Parameter covariance of every fit from the model Jacobian at `popt` (DEVICE pointers, asynchronous on `stream`;
  * uses model, n_param, dim0, dim1, n_fits, xaxis of the descriptor).  pcov is [n_fits, n_param, n_param].
  *   DPHLM_COV_JTJ   pinv(J^T J) of the unweighted Jacobian: the `pcov` curve_fit returns (lm.py:672-677)

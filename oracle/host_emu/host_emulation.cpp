@@ -127,10 +127,7 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
     std::vector<double> backing(4 * stride);  // double: 8-byte aligned storage
     float* cx = reinterpret_cast<float*>(backing.data());
     float* cy = cx + stride;
-    for (int i = 0; i < M; ++i) {
-        if (xaxis) { cx[i] = xaxis[i]; cy[i] = float(i); }  // 1-D data: cy = bin index
-        else { cx[i] = float(i % w); cy[i] = float(i / w); }
-    }
+    for (int i = 0; i < stride; ++i) fill_coords<Mo>(cx, cy, i, h, w, xaxis);
     std::vector<double> ybuf(stride), ebuf(Mo::NE * stride);
     float* y = reinterpret_cast<float*>(ybuf.data());
     float* e = reinterpret_cast<float*>(ebuf.data());

@@ -21,7 +21,7 @@ from oracle.golden import GOLDEN_DIR, load_golden  # noqa: E402
 
 
 def main():
-    names = sys.argv[1:] or sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    names = sys.argv[1:] or sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and not f.startswith("x_"))
     host_emu.build()
     for name in names:
         g = load_golden(name)
