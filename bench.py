@@ -175,10 +175,20 @@ def main():
     ap.add_argument("--group-lanes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample SM clocks through NVML (diagnostic)")
+    ap.add_argument("--workload", default="c2", help="c2 = the headline configuration (default); c3, c4, c4ls, c5, c6, c9: the other "
+                    "BASELINE / SURVEY configurations, one GPU, one informational line each (scripts/bench_configs.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "c2":
+        sys.path.insert(0, os.path.join(REPO, "scripts"))
+        import bench_configs
+
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps(bench_configs.run(args.workload, steps=min(args.steps, 10), warmup=args.warmup,
+                                               fits=None if args.fits == N_FITS else args.fits, group_lanes=args.group_lanes)))
+        return
 
     import torch
     import torch.distributed as dist
@@ -362,7 +372,8 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        dph.curve_fit_batch(models.gauss2d, h_u16, h_sets[0][1], "mle", device=local, out=h_out)
+        dph.curve_fit_batch(models.gauss2d, h_u16, h_sets[0][1], "mle", device=local, out=h_outs[i], wait=False)
+    dph.host_wait(local)
     barrier()
     t_u16 = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:

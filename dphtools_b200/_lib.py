@@ -13,6 +13,7 @@ SYMBOLS = [
     "dphlm_desc_init", "dphlm_fit_batch", "dphlm_fit_batch_host", "dphlm_host_alloc", "dphlm_host_free",
     "dphlm_device_count", "dphlm_version", "dphlm_last_error", "dphlm_last_kernel_ms", "dphlm_covariance", "dphlm_extract_rois",
     "dphlm_join", "dphlm_call_status", "dphlm_measure_fp32_peak", "dphlm_fit_batch_host_async", "dphlm_host_wait",
+    "dphlm_guess_multi_exp",
 ]
 
 
@@ -65,6 +66,9 @@ def lib():
         L.dphlm_fit_batch_host_async.restype = ctypes.c_int
         L.dphlm_host_wait.argtypes = [ctypes.c_int]
         L.dphlm_host_wait.restype = ctypes.c_int
+        L.dphlm_guess_multi_exp.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                            ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+        L.dphlm_guess_multi_exp.restype = ctypes.c_int
         L.dphlm_covariance.argtypes = [ctypes.POINTER(Desc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.dphlm_covariance.restype = ctypes.c_int
         L.dphlm_extract_rois.argtypes = [ctypes.POINTER(ExtractDesc), ctypes.c_void_p]

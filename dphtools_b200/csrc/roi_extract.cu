@@ -77,7 +77,71 @@ __global__ void __launch_bounds__(128) extract_kernel(const dphlm_extract_desc d
     }
 }
 
+// Initial guess of multi_exp_fit (dphtools/utils/fitfuncs.py:63-80, 131-152) for a batch of histograms on one x axis: per
+// segment of the x range (the reference's log-spaced split, the same for every histogram and passed in as bin bounds) a
+// log-linear estimate of (amplitude, rate, offset): offset = min, straight line through log(data - offset) over the bins
+// where that is finite, mirrored for a rising segment; the offsets of all but the last segment are dropped.  One warp per
+// histogram, float64 sums (np.polyfit of degree 1 = the closed-form regression).
+__global__ void __launch_bounds__(128) guess_multi_exp_kernel(const float* __restrict__ data, const float* __restrict__ xaxis,
+                                                              const int* __restrict__ bounds, int n_seg, int with_offset, int M,
+                                                              long long n, float* __restrict__ p0) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float* y = data + row * M;
+    const int P = 2 * n_seg + (with_offset ? 1 : 0);
+    for (int sgm = 0; sgm < n_seg; ++sgm) {
+        const int lo = bounds[sgm], hi = bounds[sgm + 1];
+        double amp = 0.0, rate = 0.0, off = 0.0;
+        if (hi > lo) {
+            const float sign = y[lo] >= y[hi - 1] ? 1.0f : -1.0f;  // rising: estimate the mirrored decay
+            float vmin = 3.4e38f;
+            for (int i = lo + lane; i < hi; i += 32) vmin = fminf(vmin, sign * y[i]);
+            for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            double s0 = 0.0, sx = 0.0, sl = 0.0, sxx = 0.0, sxl = 0.0;
+            for (int i = lo + lane; i < hi; i += 32) {
+                const double d = double(sign * y[i]) - double(vmin);
+                if (d > 0.0) {
+                    const double l = log(d), x = double(xaxis[i]);
+                    s0 += 1.0; sx += x; sl += l; sxx += x * x; sxl += x * l;
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, o); sx += __shfl_xor_sync(0xffffffffu, sx, o);
+                sl += __shfl_xor_sync(0xffffffffu, sl, o); sxx += __shfl_xor_sync(0xffffffffu, sxx, o);
+                sxl += __shfl_xor_sync(0xffffffffu, sxl, o);
+            }
+            const double den = s0 * sxx - sx * sx;
+            double m = 0.0, b = 0.0;
+            if (den != 0.0) { m = (s0 * sxl - sx * sl) / den; b = (sl - m * sx) / s0; }
+            amp = double(sign) * exp(b); rate = -m; off = double(sign) * double(vmin);
+            if (!(amp == amp)) amp = 0.0;  // nan_to_num
+            if (!(rate == rate)) rate = 0.0;
+            amp = fmin(fmax(amp, -3.0e38), 3.0e38); rate = fmin(fmax(rate, -3.0e38), 3.0e38);
+        }
+        if (lane == 0) {
+            p0[row * P + 2 * sgm] = float(amp);
+            p0[row * P + 2 * sgm + 1] = float(rate);
+            if (with_offset && sgm == n_seg - 1) p0[row * P + 2 * n_seg] = float(off);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int dphlm_guess_multi_exp(const float* data, const float* xaxis, const int32_t* seg_bounds, int32_t components, int32_t with_offset,
+                                     int32_t n_bins, int64_t n_fits, float* p0, void* stream) {
+    using dphlm::fail;
+    if (n_fits < 0 || n_bins < 1 || components < 1 || components > 3) return fail("bad shape: 1..3 components, n_bins >= 1");
+    if (n_fits == 0) return 0;
+    if (!data || !xaxis || !seg_bounds || !p0) return fail("null data/xaxis/seg_bounds/p0 pointer");
+    const long long grid = (n_fits * 32 + 127) / 128;
+    guess_multi_exp_kernel<<<(unsigned)grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(data, xaxis, seg_bounds, components, with_offset,
+                                                                                        n_bins, n_fits, p0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("guess_multi_exp_kernel launch: ") + cudaGetErrorString(e));
+    return 0;
+}
 
 extern "C" int dphlm_extract_rois(const dphlm_extract_desc* d, void* stream) {
     using dphlm::fail;

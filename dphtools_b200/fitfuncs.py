@@ -70,12 +70,67 @@ def exponent_fit(data, xdata=None, offset=True):
     return multi_exp_fit(data, xdata, components=1, offset=offset)
 
 
-def multi_exp_fit_batch(data, xdata, components, offset=True, method="mle", **kwargs):
-    """Batched :func:`multi_exp_fit` for ``[N, M]`` finite histograms on a shared x axis: per-row guesses with the
-    reference's recipe, then one :func:`curve_fit_batch` call.  Returns ``(BatchResult, p0)``."""
-    data = np.asarray(data, dtype=np.float32)
+def guess_multi_exp_batch(data, xdata, components, offset=True):
+    """:func:`guess_multi_exp` for ``[N, M]`` finite histograms on a shared x axis, on the device (``dphlm_guess_multi_exp``):
+    the segment split is computed once on the host (it depends on the x axis only), the per-segment log-linear estimates run
+    one warp per histogram.  ``data``: CUDA tensor (stays on the device) or numpy array; returns a CUDA tensor ``[N, P]``."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+
     xdata = np.asarray(xdata, dtype=np.float64)
-    if not np.isfinite(data).all():
-        raise ValueError("multi_exp_fit_batch needs finite data (mask NaNs per histogram with multi_exp_fit)")
-    p0 = np.stack([guess_multi_exp(row.astype(float), xdata, components, offset) for row in data]).astype(np.float32)
-    return curve_fit_batch(multi_exp, data, p0, method, xdata.astype(np.float32), **kwargs), p0
+    d = torch.as_tensor(data)
+    d = (d if d.is_cuda else d.cuda()).float().contiguous()
+    n, m = d.shape
+    if xdata.shape != (m,):
+        raise ValueError("xdata must have shape (M,)")
+    cuts = [0 if s.start is None else int(s.start) for s in _segments(xdata, components)] + [m]
+    bounds = torch.tensor(cuts, dtype=torch.int32, device=d.device)
+    xa = torch.as_tensor(xdata.astype(np.float32), device=d.device)
+    p0 = torch.empty((n, 2 * components + (1 if offset else 0)), dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        rc = _lib.lib().dphlm_guess_multi_exp(d.data_ptr(), xa.data_ptr(), bounds.data_ptr(), components, int(bool(offset)), m, n,
+                                              p0.data_ptr(), ctypes.c_void_p(torch.cuda.current_stream(d.device).cuda_stream))
+    if rc != 0:
+        raise RuntimeError("dphlm: " + _lib.last_error())
+    return p0
+
+
+def multi_exp_fit_batch(data, xdata, components, offset=True, method="mle", **kwargs):
+    """Batched :func:`multi_exp_fit` for ``[N, M]`` histograms on a shared x axis: the reference's guess recipe on the device
+    (:func:`guess_multi_exp_batch`), then one :func:`curve_fit_batch` call, everything on the GPU (a numpy ``data`` is uploaded
+    once; the results come back as numpy arrays then).  Histograms with non-finite bins -- the reference masks those bins per
+    histogram (``fitfuncs.py:124-126``), which changes that histogram's length -- are fitted one by one with
+    :func:`multi_exp_fit` afterwards (``info = -100`` marks them in the batch result until then; failures leave NaN).
+    Returns ``(BatchResult, p0)``."""
+    import torch
+
+    as_numpy = not (type(data).__module__.split(".")[0] == "torch")
+    d = torch.as_tensor(data)
+    d = (d if d.is_cuda else d.cuda()).float().contiguous()
+    xdata = np.asarray(xdata, dtype=np.float64)
+    finite = torch.isfinite(d).all(dim=1)
+    clean = torch.where(finite[:, None], d, torch.ones_like(d)) if not bool(finite.all()) else d
+    p0 = guess_multi_exp_batch(clean, xdata, components, offset)
+    res = curve_fit_batch(multi_exp, clean, p0, method, xdata.astype(np.float32), **kwargs)
+    bad = torch.nonzero(~finite).flatten().tolist()
+    if bad:
+        res.info[~finite] = -100
+        res.popt[~finite] = float("nan")
+        host = d[~finite].cpu().numpy().astype(float)
+        single = {k: v for k, v in kwargs.items() if k in ("ftol", "xtol", "gtol", "maxfev", "factor")}
+        for row, i in zip(host, bad):
+            try:
+                popt, _, infodict, _, ier = multi_exp_fit(row, xdata, components, offset, method=method, full_output=True, **single)
+            except (RuntimeError, ValueError, TypeError):
+                continue
+            res.popt[i] = torch.as_tensor(popt, dtype=torch.float32)
+            res.info[i], res.nfev[i] = int(ier), int(infodict["nfev"])
+            res.chisq[i] = float(infodict.get("chisq", float("nan")))
+    if as_numpy:
+        torch.cuda.synchronize(d.device)
+        res = type(res)(*[None if v is None else v.cpu().numpy() for v in res])
+        p0 = p0.cpu().numpy()
+    return res, p0

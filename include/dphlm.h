@@ -151,6 +151,14 @@ typedef struct dphlm_extract_desc {
 } dphlm_extract_desc;
 int dphlm_extract_rois(const dphlm_extract_desc* d, void* stream);
 
+/* Initial guesses of multi_exp_fit (dphtools/utils/fitfuncs.py:63-80, 131-152) for n_fits histograms [n_fits, n_bins] on the
+ * shared x axis, on the device: per component one segment of the x range -- bins [seg_bounds[k], seg_bounds[k+1]), the
+ * reference's log-spaced split, computed once by the caller (DEVICE pointer to components + 1 ints) -- and in each segment
+ * the log-linear estimate (amplitude, rate, offset) of _estimate_exponent_params; p0 is [n_fits, 2 components (+ 1)], the
+ * layout dphlm_fit_batch takes for DPHLM_MULTI_EXP.  The data must be finite.  Asynchronous on `stream`. */
+int dphlm_guess_multi_exp(const float* data, const float* xaxis, const int32_t* seg_bounds, int32_t components, int32_t with_offset,
+                          int32_t n_bins, int64_t n_fits, float* p0, void* stream);
+
 /* Page-locked host buffers for dphlm_fit_batch_host (plain malloc'ed memory works too, slower). */
 void* dphlm_host_alloc(size_t bytes);
 void dphlm_host_free(void* p);

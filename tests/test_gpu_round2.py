@@ -149,3 +149,55 @@ def test_in_process_multi_device_launcher_equals_one_device(golden):
     many = dph.curve_fit_batch(models.gauss2d, g["data"], g["p0"], "mle", device=devices)
     for k in ("popt", "info", "nfev", "chisq"):
         np.testing.assert_array_equal(getattr(one, k), getattr(many, k))
+
+
+def test_async_host_calls_equal_blocking_calls(golden):
+    """dphlm_fit_batch_host_async + dphlm_host_wait: several batches enqueued back to back from page-locked buffers (the upload of
+    one overlaps the kernels of the one before), one wait, same results as one blocking call per batch."""
+    g = golden("c2_mle")
+    n = 4000
+    ins, outs = [], []
+    for k in range(3):
+        hd, hp = dph.pinned_empty((n, 11, 11)), dph.pinned_empty((n, 5))
+        hd[...] = g["data"][k * 2000:k * 2000 + n]
+        hp[...] = g["p0"][k * 2000:k * 2000 + n]
+        ins.append((hd, hp))
+        outs.append(dph.BatchResult(dph.pinned_empty((n, 5)), dph.pinned_empty(n, np.int32), dph.pinned_empty(n, np.int32),
+                                    dph.pinned_empty(n), None, None))
+    for (hd, hp), o in zip(ins, outs):
+        dph.curve_fit_batch(models.gauss2d, hd, hp, "mle", device=0, out=o, wait=False)
+    dph.host_wait(0)
+    for (hd, hp), o in zip(ins, outs):
+        ref = dph.curve_fit_batch(models.gauss2d, hd, hp, "mle", device=0)
+        for k in ("popt", "info", "nfev", "chisq"):
+            np.testing.assert_array_equal(getattr(o, k), getattr(ref, k))
+    dph.host_wait(0)  # nothing pending: returns at once
+
+
+def test_device_guess_is_the_reference_recipe_and_the_batch_driver_runs_on_the_gpu(golden):
+    """dphlm_guess_multi_exp against the host restatement of multi_exp_fit's guess (fitfuncs.py:63-80, 131-152; identical to the
+    live reference, tests/test_host_api.py), then multi_exp_fit_batch end to end, including histograms with non-finite bins,
+    which the reference masks per histogram (fitfuncs.py:124-126)."""
+    from dphtools_b200 import fitfuncs
+
+    g = golden("c5_mle")
+    t = g["xaxis"].astype(float)[1:]  # t > 0 for the log-spaced split
+    data = g["data"][:300, 1:]
+    for comps, off in ((2, True), (1, True), (2, False), (3, True)):
+        want = np.stack([fitfuncs.guess_multi_exp(row.astype(float), t, comps, off) for row in data])
+        got = fitfuncs.guess_multi_exp_batch(data, t, comps, off).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=1e-5)
+    dirty = data.copy()
+    dirty[5, 40] = np.nan
+    dirty[17, 3] = np.inf
+    res, p0 = fitfuncs.multi_exp_fit_batch(dirty, t, 2, method="mle")
+    clean, _ = fitfuncs.multi_exp_fit_batch(torch.from_numpy(data).cuda(), t, 2, method="mle")
+    assert isinstance(res.popt, np.ndarray) and clean.popt.is_cuda
+    keep = np.ones(300, bool)
+    keep[[5, 17]] = False
+    np.testing.assert_array_equal(res.popt[keep], clean.popt.cpu().numpy()[keep])
+    assert ((res.info >= 1) & (res.info <= 4)).mean() > 0.99
+    for i in (5, 17):  # fitted alone on their finite bins, like the reference does
+        want, _ = fitfuncs.multi_exp_fit(dirty[i].astype(float), t, components=2, method="mle")
+        np.testing.assert_allclose(res.popt[i], want, rtol=1e-5)
+        np.testing.assert_allclose(res.popt[i], clean.popt[i].cpu().numpy(), rtol=0.2)  # one bin fewer: nearly the same fit
