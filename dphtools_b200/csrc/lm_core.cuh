@@ -41,7 +41,7 @@
 #define DPH_TIE_BREAK 0  // float64 gradient for xtol ties (precise_gradient): experimental, off
 #endif
 #ifndef DPH_PAIR_UNROLL
-#define DPH_PAIR_UNROLL 1  // unroll factor of the pixel-pair loop (registers vs instruction-level parallelism)
+#define DPH_PAIR_UNROLL 2  // unroll factor of the pixel-pair loop: two pairs in flight per lane (fits the register bound since the stash)
 #endif
 
 namespace dphlm {
@@ -289,8 +289,11 @@ DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
 // the model value, its Jacobian row, the accurate step difference delta() and J(x_old).d .
 // Pixel coordinates arrive as (cx, cy); 1-D models use cx only.
 
+#ifndef DPH_GAUSS2D_MINCTAS
+#define DPH_GAUSS2D_MINCTAS 3
+#endif
 struct Gauss2D {  // amp, x0, y0, sigma, offset
-    static constexpr int P = 5, NE = 1, kMinCtas = 3;
+    static constexpr int P = 5, NE = 1, kMinCtas = DPH_GAUSS2D_MINCTAS;
     struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3, ad1, ad2, anh; };  // a*: step from / exponent scale of the accepted point
     struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
     template <class T> struct Geo { T dx, dy, r2; };
@@ -895,6 +898,7 @@ struct PixelState {
     int cur;
     float* tbl = nullptr;  // Mo::table_floats(h, w): per-trial tables of models that need them (fill_tables), else unused
     int w = 1;             // row length of a 2-D ROI (M / w rows)
+    float* stash = nullptr;  // kStashFloats per group: where the per-fit scalars the pixel loop does not need wait during a pass
     DPH_HD float* ebuf(int which, int j) const { return e + (which * NE + j) * stride; }
 };
 
@@ -913,6 +917,26 @@ DPH_HD void fill_coords(float* cx, float* cy, int k, int h, int w, const float* 
     (void)h;
     cx[k] = xaxis ? xaxis[i] : float(i % w);
     cy[k] = xaxis ? float(i) : float(i / w);
+}
+
+// Per-fit scalars that the pixel loop does not touch (the normal equations of the accepted point, its gradient, the scaling
+// and the step: 30 floats for 5 parameters) are parked in the group's shared memory for the duration of a pass and read back
+// after it.  The pass runs at the register bound of three CTAs per SM; without this the compiler recomputes loop-invariant
+// step constants inside the loop instead of keeping them (DPH_STASH=0 builds the old form).
+#ifndef DPH_STASH
+#define DPH_STASH 1
+#endif
+// floats per group: everything (30 for 5 parameters) where shared memory allows it; the normal equations alone for two-lane
+// groups (64 fits per CTA leave 19 floats per group before a third CTA no longer fits on the SM) and for models that keep
+// per-pixel values of the accepted point in shared memory (measured: the full size costs the fixed-width Gaussian its third CTA)
+DPH_HD constexpr int stash_floats(int G, bool store_e) { return G >= 4 && !store_e ? 32 : 16; }
+DPH_HD void stash_store(float* s, const float* v, int n) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) s[i] = v[i];
+}
+DPH_HD void stash_load(const float* s, float* v, int n) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) v[i] = *reinterpret_cast<const volatile float*>(s + i);
 }
 
 // Group of G lanes.  On the host G == 1 and the reductions are the identity.
@@ -1400,6 +1424,16 @@ struct StageA {
     }
     DPH_HD int propose_precise(const Options&, const double*, float*) { return 1; }
     DPH_HD const float* xlo_ptr() const { return x; }
+    // what waits in the group's shared memory during a pass: A always, g, D and the step if `cap` floats hold them too
+    static constexpr bool kStash = DPH_STASH && NTP <= 16;
+    template <int CAP> DPH_HD void stash_put(float* s, const float* p) const {
+        stash_store(s, A, NTP);
+        if (NTP + 3 * P <= CAP) { stash_store(s + NTP, g, P); stash_store(s + NTP + P, D, P); stash_store(s + NTP + 2 * P, p, P); }
+    }
+    template <int CAP> DPH_HD void stash_get(const float* s, float* p) {
+        stash_load(s, A, NTP);
+        if (NTP + 3 * P <= CAP) { stash_load(s + NTP, g, P); stash_load(s + NTP + P, D, P); stash_load(s + NTP + 2 * P, p, P); }
+    }
     // new Jacobian at an accepted point: gradient test and rescaling (lmder.f: gnorm, diag = max(diag, wa2))
     DPH_HD void fresh(const Options& opt) {
         if (opt.gtol > 0.0f && chi > 0.0f) {
@@ -1563,6 +1597,15 @@ struct StageB {
         return r;
     }
     DPH_HD const float* xlo_ptr() const { return xlo; }
+    static constexpr bool kStash = DPH_STASH && NTP <= 16;
+    template <int CAP> DPH_HD void stash_put(float* s, const float* p) const {
+        stash_store(s, A, NTP);
+        if (NTP + 3 * P <= CAP) { stash_store(s + NTP, g, P); stash_store(s + NTP + P, dtd, P); stash_store(s + NTP + 2 * P, p, P); }
+    }
+    template <int CAP> DPH_HD void stash_get(const float* s, float* p) {
+        stash_load(s, A, NTP);
+        if (NTP + 3 * P <= CAP) { stash_load(s + NTP, g, P); stash_load(s + NTP + P, dtd, P); stash_load(s + NTP + 2 * P, p, P); }
+    }
     DPH_HD int solve_step(const Options& opt, const float* gg, float* p, bool tie) {
         float U[NTP], d[P];
         bool ok = chol_factor<P>(A, dtd, lam, U);
@@ -1719,6 +1762,7 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         // models with per-trial tables; no-op otherwise.  Last argument: bit 0 = which buffer holds the accepted point, bit 1 = first pass
         Mo::fill_tables(ln, st.q0, q1, step, px.tbl, px.M / px.w, px.w, px.cur | (st.init ? 2 : 0));
         const bool init = st.init, want_chi = Lanes<G>::warp_any(pass && st.wants_chi());
+        if (Stage::kStash) st.template stash_put<stash_floats(G, Mo::kStoreE)>(px.stash, p);
         trial_pass<Mo, Stage::kMle, Stage::kPred, true, G>(ln, px, st.q0, q1, step, init, want_chi, nrm);
         // the branch-free pass is valid only between two regular points; otherwise repeat it in the literal form
         const bool trial_irregular = Stage::kMle && (nrm.flags & kFlagIrregular);
@@ -1728,6 +1772,7 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
             trial_pass<Mo, Stage::kMle, Stage::kPred, false, G>(ln, px, st.q0, q1, step, init, want_chi, slow);
             if (literal) nrm = slow;
         }
+        if (Stage::kStash) st.template stash_get<stash_floats(G, Mo::kStoreE)>(px.stash, p);
         if (pass) {
             bool accepted;
             const bool done = st.consume(opt, nrm, p, q1, accepted);

@@ -381,7 +381,7 @@ struct IoDevice {
 
 // shared-memory floats of one lane group: two data buffers (working + staged, each with the extra
 // words) and the double-buffered exponentials
-__host__ __device__ inline int group_region(int stride, int ne, int table = 0) { return 2 * (stride + kStageExtra) + 2 * ne * stride + table; }
+__host__ __device__ inline int group_region(int stride, int ne, int table, int G) { return 2 * (stride + kStageExtra) + 2 * ne * stride + table + stash_floats(G, ne > 0); }
 
 // CTAs per SM the register allocation is bounded for: 3 (<= 168 registers) where that costs no spills (the symmetric
 // Gaussian, single exponentials); models with more parameters or more per-pixel state declare kMinCtas = 2 (<= 255
@@ -403,11 +403,12 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G;
     const int table = Mo::table_floats(a.h, a.w);
-    const int region = group_region(stride, Mo::kStoreE ? Mo::NE : 0, table);
+    const int region = group_region(stride, Mo::kStoreE ? Mo::NE : 0, table, G);
     float* base = smem + 2 * ((M + 1) & ~1) + (warp * FPW + grp) * region;
     Lanes<G> ln{lane % G, G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (grp * G))};
     PixelState<Mo::NE> px{base, base + 2 * (stride + kStageExtra), cx, cy, M, stride, 0};
-    px.tbl = base + region - table;
+    px.tbl = base + region - table - stash_floats(G, Mo::kStoreE);
+    px.stash = base + region - stash_floats(G, Mo::kStoreE);
     px.w = a.w;
     IO io{a, base + stride + kStageExtra};
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
@@ -674,8 +675,8 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     const bool skip_prefit = a0.skip_prefit != 0;  // lm() alone: p_ls aliases p0, every pre-fit exit code starts as 1
     const int M = a0.h * a0.w;
     constexpr int FPW = 32 / G;
-    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w)));
-    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w)));
+    const size_t smem = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * FPW * group_region(padded_stride(M, G), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w), G));
+    const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w), 32));
     const bool handoff = G < 32 && pl.cap > 0;
     const int kPollerCtas = budget_from_env("DPHLM_POLLER_CTAS", kPollerCtasDefault);  // tuning aid
     using SA = StageA<Mo>;

@@ -136,6 +136,8 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
     std::vector<double> table(Mo::table_floats(h, w) / 2 + 2);  // double: 16-byte aligned by operator new
     px.tbl = reinterpret_cast<float*>(table.data());
     px.w = w;
+    float stash[32];
+    px.stash = stash;
     if (b.skip_prefit) {
         for (long i = 0; i < b.n; ++i) {
             b.ier[i] = 1;
