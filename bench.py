@@ -310,16 +310,28 @@ def main():
     h_probe = torch.from_numpy(dph.pinned_empty(n * (ROI * ROI + 5)))  # the allocator the e2e leg uses (cudaHostAlloc)
     h_probe.zero_()
     d_probe = torch.empty_like(h_probe, device=dev)
+    probe_streams = [torch.cuda.Stream(device=dev) for _ in range(4)]  # four copies in flight, like the host entry's chunks
+    quarter = h_probe.numel() // 4
+
+    def probe_round():
+        for k, st_ in enumerate(probe_streams):
+            with torch.cuda.stream(st_):
+                d_probe[k * quarter:(k + 1) * quarter].copy_(h_probe[k * quarter:(k + 1) * quarter], non_blocking=True)
+
     for _ in range(2):
-        d_probe.copy_(h_probe, non_blocking=True)
+        probe_round()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    for st_ in probe_streams:
+        st_.wait_event(ev0)
     for _ in range(8):
-        d_probe.copy_(h_probe, non_blocking=True)
+        probe_round()
+    for st_ in probe_streams:
+        torch.cuda.current_stream().wait_stream(st_)
     ev1.record()
     barrier()
-    h2d_gbs = torch.tensor([8 * h_probe.numel() * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9], device=dev)
+    h2d_gbs = torch.tensor([8 * 4 * quarter * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9], device=dev)
     if world > 1:
         dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
     h2d_gbs = float(h2d_gbs.item())

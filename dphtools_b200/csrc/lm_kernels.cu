@@ -394,8 +394,11 @@ static int host_enqueue(const dphlm_desc* d, int device) {
             s.cap = need;
         }
     }
-    int k = 0;
-    for (size_t ci = 0; ci + 1 < bounds.size() && rc == 0; ++ci, k = (k + 1) % kHostSlots) {
+    int n_slots = kHostSlots;  // 8 against 4: consecutive calls land on different slots (+4 % end to end at 1e5 fits per call)
+    if (const char* e = getenv("DPHLM_HOST_SLOTS")) n_slots = std::min(std::max(atoi(e), 1), (int)kHostSlots);  // tuning aid
+    static unsigned next_slot[64];  // round-robin across calls too (under host_mu)
+    int k = next_slot[device] % n_slots;
+    for (size_t ci = 0; ci + 1 < bounds.size() && rc == 0; ++ci, k = (k + 1) % n_slots) {
         const long long lo = bounds[ci], n = bounds[ci + 1] - lo;
         auto& s = ctx->slots[k];
         char* b = s.buf;
@@ -442,6 +445,7 @@ static int host_enqueue(const dphlm_desc* d, int device) {
         if (d->counts) CUDA_TRY(cudaMemcpyAsync(d->counts + lo * 4, dcnt, n * 16, cudaMemcpyDeviceToHost, s.stream));
         if (d->x_acc) CUDA_TRY(cudaMemcpyAsync(d->x_acc + lo * P, dxacc, n * P * 4, cudaMemcpyDeviceToHost, s.stream));
     }
+    next_slot[device] = (unsigned)k;
     cudaSetDevice(prev);
     return rc;
 }

@@ -556,7 +556,7 @@ int launch_cov(const CovArgs& a, cudaStream_t stream) {
     return 0;
 }
 
-constexpr int kHostSlots = 4;  // chunks in flight on the host path
+constexpr int kHostSlots = 8;  // staging slots of the host path (DPHLM_HOST_SLOTS of them are used: chunks in flight)
 
 struct DeviceCtx {
     std::mutex mu;
