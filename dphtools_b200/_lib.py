@@ -97,6 +97,7 @@ FLAG_NO_HANDOFF = 2
 FLAG_DATA_U16 = 4
 FLAG_PIPELINED = 8
 FLAG_SKIP_PREFIT = 16
+FLAG_EXACT_TIES = 32
 INFO_UNFINISHED = -2139062144  # DPHLM_INFO_UNFINISHED
 
 

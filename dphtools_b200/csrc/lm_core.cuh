@@ -30,15 +30,14 @@
 
 #if defined(__CUDACC__)
 #define DPH_HD __host__ __device__ __forceinline__
+#define DPH_HD_COLD __host__ __device__ __noinline__  // rarely executed code that must not weigh on the callers' registers
 #else
 #define DPH_HD inline
+#define DPH_HD_COLD inline
 #endif
 
 #ifndef DPH_GAUSS2D_STORE
 #define DPH_GAUSS2D_STORE false
-#endif
-#ifndef DPH_TIE_BREAK
-#define DPH_TIE_BREAK 0  // float64 gradient for xtol ties (precise_gradient): experimental, off
 #endif
 #ifndef DPH_PAIR_UNROLL
 #define DPH_PAIR_UNROLL 2  // unroll factor of the pixel-pair loop: two pairs in flight per lane (fits the register bound since the stash)
@@ -326,7 +325,7 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
         T t = e[0] * T(q.as2);
         J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = e[0] * T(q.as3) * g.r2; J[4] = T(1.0f);
     }
-    // float64 model value and Jacobian row at one pixel (the tie-break pass of StageB, see precise_gradient)
+    // float64 model value and Jacobian row at one pixel (the tie-break pass of StageB, see precise_normal; the covariance kernel)
     DPH_HD static void eval64(const double* p, const float*, double cx, double cy, double& f, double* J) {
         const double dx = cx - p[1], dy = cy - p[2], r2 = dx * dx + dy * dy, s2 = p[3] * p[3];
         const double e = exp(-r2 / (2.0 * s2)), ae = p[0] * e;
@@ -1258,44 +1257,95 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
 }
 
 // ---------------------------------------------------------------------------------- tie-break pass
-// The reference ends lm() with info = 2 when |dx| <= xtol (|x| + xtol) with xtol = 1.49e-8 (lm.py:365-367, 430-432): a
-// step four times smaller than float32 resolves in x itself.  Whether that test fires is decided by the gradient at the
-// accepted point to ~1e-9 of its scale, which neither a float32 x (rounding the accepted point moves the Newton step by the
-// rounding error) nor a float32 model value (ex2.approx alone is 2e-7) can deliver; left alone, the fits whose last step is
-// within a factor ~8 of the threshold -- 1-3 % of a batch -- get a coin flip between info 1 and info 2.  For exactly those
-// trips, and only for them, the gradient is recomputed in float64 at the accepted point kept as a float32 pair (x + xlo, the
-// rounding error of x <- x + d is kept), and the test is repeated with the step from that gradient.  This is the one place
-// float64 is used; it costs one extra pass for ~2 % of the fits and nothing otherwise.
+// The reference ends lm() with info = 2 when |dx| <= xtol (|x| + xtol), xtol = 1.49e-8 (lm.py:365-367, 430-432): a step four
+// times smaller than float32 resolves in x itself.  Whether that test fires is decided by the Newton step at the accepted
+// point to ~1e-9 |x|, and the float32 trajectory carries ~3e-8 |x| of noise into that point (the gradient of the previous
+// trip, summed from float32 model values, moved it by that much).  Left alone, the fits whose last step is within a small
+// factor of the threshold -- up to 2 % of a batch for the 4-parameter models -- get a coin flip between info 1 and info 2.
+// With Options::exact_ties a proposal within kTieBand of the threshold is re-decided in float64 (the one place float64 is
+// used): the previous accepted point (kept in the working buffer's spare words) is taken as exact, its normal equations and
+// gradient are summed in float64 and the damped step from there is repeated -- that removes the noise the float32 gradient
+// put into the accepted point -- and the test is made with the float64 step at the point so reached.  Measured on the
+// golden sets: info equality 98.0 -> 99.8 % (4-parameter models), 99.85 -> 99.95 % (5 parameters); cost: two float64 passes
+// for the ~5 % of the fits that come that close.
 template <class Mo, bool MLE, int G>
-DPH_HD void precise_gradient(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const float* x, const float* xlo, const float* consts,
-                             double* g) {
+DPH_HD void precise_normal(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const double* p, const float* consts, double* A, double* g) {
     constexpr int P = Mo::P;
-    double p[P];
 #pragma unroll
-    for (int k = 0; k < P; ++k) { p[k] = double(x[k]) + double(xlo[k]); g[k] = 0.0; }
+    for (int k = 0; k < NT<P>::value; ++k) A[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < P; ++k) g[k] = 0.0;
     for (int i = ln.lane; i < px.M; i += G) {
         double f, J[P];
         Mo::eval64(p, consts, double(px.cx[i]), double(px.cy[i]), f, J);
         const double y = double(px.y[i]);  // MLE: clamped when the fit was staged (lm.py:127)
-        double res;
+        double w = 1.0, res;
         if (MLE) {
             if (f <= 0.0) f = 0.0;  // lm.py:132
             const double yf = y / f, yf2 = yf / f;
-            res = (yf - yf == 0.0 && yf2 - yf2 == 0.0) ? 1.0 - yf : 1.0;  // lm.py:86-102: invalid pixel -> residual 1
+            const bool ok = (yf - yf == 0.0) && (yf2 - yf2 == 0.0);  // lm.py:86-102: invalid pixel -> weight 0, residual 1
+            w = ok ? yf2 : 0.0;
+            res = ok ? 1.0 - yf : 1.0;
         } else {
             res = f - y;
         }
 #pragma unroll
-        for (int k = 0; k < P; ++k) g[k] += J[k] * res;
+        for (int r = 0; r < P; ++r) {
+            const double wj = w * J[r];
+#pragma unroll
+            for (int c = r; c < P; ++c) A[tri<P>(r, c)] += wj * J[c];
+            g[r] += J[r] * res;
+        }
     }
 #pragma unroll
+    for (int k = 0; k < NT<P>::value; ++k) A[k] = ln.sum_group(A[k]);
+#pragma unroll
     for (int k = 0; k < P; ++k) g[k] = ln.sum_group(g[k]);
+}
+
+// d = -(A + lam diag(D))^-1 g in float64 (Cholesky); false if the matrix is not positive definite
+template <int P>
+DPH_HD bool solve_damped64(const double* A, const float* D, double lam, const double* g, double* d) {
+    double U[NT<P>::value];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        double piv = A[tri<P>(i, i)] + lam * double(D[i]);
+#pragma unroll
+        for (int k = 0; k < i; ++k) piv -= U[tri<P>(k, i)] * U[tri<P>(k, i)];
+        if (!(piv > 0.0)) return false;
+        const double r = 1.0 / sqrt(piv);
+        U[tri<P>(i, i)] = r;
+#pragma unroll
+        for (int j = i + 1; j < P; ++j) {
+            double t = A[tri<P>(i, j)];
+    #pragma unroll
+        for (int k = 0; k < i; ++k) t -= U[tri<P>(k, i)] * U[tri<P>(k, j)];
+            U[tri<P>(i, j)] = t * r;
+        }
+    }
+    double z[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        double t = -g[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) t -= U[tri<P>(k, i)] * z[k];
+        z[i] = t * U[tri<P>(i, i)];
+    }
+#pragma unroll
+    for (int i = P - 1; i >= 0; --i) {
+        double t = z[i];
+#pragma unroll
+        for (int k = i + 1; k < P; ++k) t -= U[tri<P>(i, k)] * d[k];
+        d[i] = t * U[tri<P>(i, i)];
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------- options/result
 struct Options {
     float ftol, xtol, gtol, factor;
-    int maxfev;  // <= 0: 100 * (P + 1)
+    int maxfev;      // <= 0: 100 * (P + 1)
+    int exact_ties;  // != 0: re-decide borderline xtol tests in float64 (precise_normal)
 };
 
 // ------------------------------------------------------------------------- stage A: MINPACK lmder
@@ -1422,8 +1472,10 @@ struct StageA {
         if (first) delta = fminf(delta, pnorm);
         return 1;
     }
-    DPH_HD int propose_precise(const Options&, const double*, float*) { return 1; }
-    DPH_HD const float* xlo_ptr() const { return x; }
+    DPH_HD void note_accepted(const float*, float*) {}
+    DPH_HD float lam_of_step() const { return 0.0f; }
+    DPH_HD int tie_fallback() { return 1; }
+    template <int G> DPH_HD int tie_break(const Lanes<G>&, const PixelState<Mo::NE>&, const Options&, const float*) { return 1; }
     // what waits in the group's shared memory during a pass: A always, g, D and the step if `cap` floats hold them too
     static constexpr bool kStash = DPH_STASH && NTP <= 16;
     template <int CAP> DPH_HD void stash_put(float* s, const float* p) const {
@@ -1534,36 +1586,42 @@ struct StageB {
     static constexpr int P = Mo::P;
     static constexpr int NTP = NT<P>::value;
     static constexpr bool kMle = MLE, kPred = true;
-    static constexpr bool kTie = MLE && DPH_TIE_BREAK;  // least squares ends at trip 0 on the pre-fit's own optimum (Q16): nothing to break
-    static constexpr float kTieBand = 8.0f;  // |dx| within this factor of the xtol threshold -> float64 gradient (precise_gradient)
-    float x[P], xlo[P], A[NTP], g[P], dtd[P], xret[P];
+    static constexpr bool kTie = MLE;  // least squares ends at trip 0 on the pre-fit's own optimum (Q16): nothing to break
+    static constexpr float kTieBand = 16.0f;  // |dx| within this factor of the xtol threshold: re-decided in float64 (Options::exact_ties)
+    float x[P], A[NTP], g[P], dtd[P], xret[P];
+    bool hist;  // the previous accepted point and its lambda are in the working buffer's spare words (note_accepted)
+    bool tie_fires;  // what float32 says about a proposal that is too close to call
     typename Mo::Par q0;
     float chisq_old, chisq_ret, lam;
-    int info, ev, n_acc, n_rej;
+    int info, ev, n_acc, n_rej, n_tie;
     bool init, live, resumed;
 
     DPH_HD void start(const float* p_ls, const float* consts = nullptr) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) { x[i] = xret[i] = p_ls[i]; xlo[i] = 0.0f; }
+        for (int i = 0; i < P; ++i) x[i] = xret[i] = p_ls[i];
+        hist = false;
         Mo::set_consts(q0, consts);
         Mo::prepare(x, q0);
         chisq_old = chisq_ret = lam = 0.0f;
-        info = 5; ev = 0; n_acc = n_rej = 0;
+        info = 5; ev = 0; n_acc = n_rej = n_tie = 0;
         init = true; live = false; resumed = false;
     }
-    static constexpr int kRecord = 3 * P + 6;
+    // continuation record: the state, then (words kKeepAt ...) whether a previous accepted point is known, that point and its lambda
+    static constexpr int kKeepAt = 3 * P + 8, kRecord = 4 * P + 9;
     DPH_HD int trips() const { return ev; }
     DPH_HD void save(float* r) const {
 #pragma unroll
         for (int i = 0; i < P; ++i) { r[i] = x[i]; r[P + i] = dtd[i]; r[2 * P + i] = xret[i]; }
         r[3 * P] = chisq_old; r[3 * P + 1] = chisq_ret; r[3 * P + 2] = lam;
         r[3 * P + 3] = float(ev); r[3 * P + 4] = float(n_acc); r[3 * P + 5] = float(n_rej);
+        r[3 * P + 6] = hist ? 1.0f : 0.0f; r[3 * P + 7] = float(n_tie);
     }
     DPH_HD void resume(const float* r, const float* consts = nullptr) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) { x[i] = r[i]; dtd[i] = r[P + i]; xret[i] = r[2 * P + i]; xlo[i] = 0.0f; }
+        for (int i = 0; i < P; ++i) { x[i] = r[i]; dtd[i] = r[P + i]; xret[i] = r[2 * P + i]; }
         chisq_old = r[3 * P]; chisq_ret = r[3 * P + 1]; lam = r[3 * P + 2];
-        ev = int(r[3 * P + 3]); n_acc = int(r[3 * P + 4]); n_rej = int(r[3 * P + 5]);
+        ev = int(r[3 * P + 3]); n_acc = int(r[3 * P + 4]); n_rej = int(r[3 * P + 5]); n_tie = int(r[3 * P + 7]);
+        hist = r[3 * P + 6] != 0.0f;  // (the caller puts the kept point back behind its working ROI)
         Mo::set_consts(q0, consts);
         Mo::prepare(x, q0);
         info = 5;
@@ -1571,7 +1629,7 @@ struct StageB {
     }
     DPH_HD bool wants_chi() const { return init && !resumed; }
     // 0: the fit ended before the evaluation (xtest / gtest), 1: evaluate x + p, 2: |dx| is within kTieBand of the xtol
-    // threshold -- the caller supplies the float64 gradient and calls propose_precise()
+    // threshold and Options::exact_ties is set -- the caller calls tie_break()
     DPH_HD int propose(const Options& opt, float* p) {
         live = false;
 #pragma unroll
@@ -1583,20 +1641,88 @@ struct StageB {
             for (int i = 0; i < P; ++i) gm = fmaxf(gm, fabsf(g[i]));
             if (gm <= opt.gtol) { info = 4; return 0; }
         }
-        return solve_step(opt, g, p, kTie);
+        return solve_step(opt, g, p);
     }
-    DPH_HD int propose_precise(const Options& opt, const double* g64, float* p) {
-        float gp[P];
+    DPH_HD float lam_of_step() const { return lam; }
+    // the float32 decision, when nobody can break the tie (the straggler list is full)
+    DPH_HD int tie_fallback() {
+        if (!tie_fires) return 1;
+        info = 2;
+        live = false;
+        return 0;
+    }
+    // the accepted point a step was just taken from and the lambda of that step: what tie_break() repeats in float64.
+    // `keep`: the P + 1 spare words behind the working ROI (free once the fit has been fetched)
+    DPH_HD void note_accepted(const float* xold_lam, float* keep) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) gp[i] = float(g64[i]);
-        const int r = solve_step(opt, gp, p, false);
-        if (r == 1 && live) {  // the step starts at x + xlo
+        for (int i = 0; i <= P; ++i) keep[i] = xold_lam[i];
+        hist = true;
+    }
+    // The proposal is within kTieBand of the xtol threshold: decide in float64.  1: evaluate the step, 0: xtest fires (info 2).
+    template <int G> DPH_HD_COLD int tie_break(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const Options& opt, const float* consts) {
+        double A64[NTP], g64[P], xp[P], d[P];
+        const volatile float* keep = px.y + px.stride;
+        ++n_tie;
+        if (hist) {  // repeat the last accepted step from the previous accepted point, exactly
 #pragma unroll
-            for (int i = 0; i < P; ++i) p[i] += xlo[i];
+            for (int i = 0; i < P; ++i) xp[i] = double(keep[i]);
+            precise_normal<Mo, MLE, G>(ln, px, xp, consts, A64, g64);
+            if (solve_damped64<P>(A64, dtd, double(keep[P]), g64, d)) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) xp[i] += d[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < P; ++i) xp[i] = double(x[i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) xp[i] = double(x[i]);
         }
-        return r;
+        precise_normal<Mo, MLE, G>(ln, px, xp, consts, A64, g64);
+        if (!solve_damped64<P>(A64, dtd, double(lam), g64, d)) return 1;  // keep the float32 decision (not firing)
+        double dn = 0.0, xn = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; ++i) { dn += d[i] * d[i]; xn += xp[i] * xp[i]; }
+        if (sqrt(dn) <= double(opt.xtol) * (sqrt(xn) + double(opt.xtol))) {  // lm.py:365-367, 430-432
+            info = 2;
+            live = false;
+            return 0;
+        }
+        return 1;
     }
-    DPH_HD const float* xlo_ptr() const { return xlo; }
+    DPH_HD int solve_step(const Options& opt, const float* gg, float* p) {
+        float U[NTP], d[P];
+        bool ok = chol_factor<P>(A, dtd, lam, U);
+        if (ok) {
+            chol_solve_neg<P>(U, gg, d);
+#pragma unroll
+            for (int i = 0; i < P; ++i) ok = ok && f_finite(d[i]);
+        }
+        if (!ok) {
+            lam *= opt.factor;  // lm.py:426-428: the trip is consumed
+            return 1;
+        }
+        float dn = 0.0f, xn2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) { dn = f_fma(d[i], d[i], dn); xn2 = f_fma(x[i], x[i], xn2); }
+        const float thr = opt.xtol * (sqrtf(xn2) + opt.xtol), dnorm = sqrtf(dn);
+        const bool fires = dnorm <= thr;  // lm.py:365-367, 430-432
+        if (kTie && opt.exact_ties && dnorm <= kTieBand * thr) {  // too close to call in float32 (also when it seems to fire)
+            tie_fires = fires;
+            live = true;
+#pragma unroll
+            for (int i = 0; i < P; ++i) p[i] = d[i];
+            return 2;
+        }
+        if (fires) {
+            info = 2;
+            return 0;
+        }
+        live = true;
+#pragma unroll
+        for (int i = 0; i < P; ++i) p[i] = d[i];
+        return 1;
+    }
     static constexpr bool kStash = DPH_STASH && NTP <= 16;
     template <int CAP> DPH_HD void stash_put(float* s, const float* p) const {
         stash_store(s, A, NTP);
@@ -1676,11 +1802,7 @@ struct StageB {
                     return true;
                 }
 #pragma unroll
-                for (int i = 0; i < P; ++i) {  // x <- fl(x + p); xlo = (x + p) - fl(x + p) exactly (TwoSum)
-                    const float sum = xret[i], bv = sum - x[i];
-                    if (kTie) xlo[i] = (x[i] - (sum - bv)) + (p[i] - bv);
-                    x[i] = sum;
-                }
+                for (int i = 0; i < P; ++i) x[i] = xret[i];
                 q0 = q1;
                 accepted = true;
                 chisq_old -= actual;
@@ -1709,6 +1831,12 @@ struct StageB {
 // and may take over a fit that has used up its trip budget (park): stragglers -- the reference's own
 // trajectories reach 100-360 trips on degenerate ROIs -- are handed to a follow-up launch where a whole
 // warp owns each fit, instead of holding a narrow group (and the tail of the kernel) for milliseconds.
+#if defined(__CUDA_ARCH__)
+template <int G> constexpr bool kTieInline = G == 32;
+#else
+template <int G> constexpr bool kTieInline = true;
+#endif
+
 template <class Stage, class Mo, int G, class IO>
 DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options& opt, IO& io) {
     constexpr int P = Mo::P;
@@ -1737,12 +1865,23 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         if (!Lanes<G>::warp_any(has)) break;
         bool pass = has;
         int proposed = has ? st.propose(opt, p) : 1;
-        if (Stage::kTie && Lanes<G>::warp_any(proposed == 2)) {  // xtol tie-break: rare (see precise_gradient)
+        if constexpr (Stage::kTie) {
+          if (Lanes<G>::warp_any(proposed == 2)) {  // xtol tie-break: rare (see precise_normal)
             if (proposed == 2) {
-                double g64[P];
-                precise_gradient<Mo, Stage::kMle, G>(ln, px, st.x, st.xlo_ptr(), io.consts(), g64);
-                proposed = st.propose_precise(opt, g64, p);
+                // The float64 passes run where a whole warp owns the fit (the poller kernels; the host build): a narrow group
+                // hands the fit over like a straggler.  Inside a narrow group they would stall the other fits of the warp for
+                // the length of ~20 ordinary trips (measured: 3x slower calls), and their code would sit in the hot kernels.
+                if constexpr (kTieInline<G>) {
+                    proposed = st.template tie_break<G>(ln, px, opt, io.consts());
+                } else if (io.park_tie(ln, px, st, fit)) {
+                    has = false;
+                    pass = false;
+                    proposed = 1;
+                } else {
+                    proposed = st.tie_fallback();
+                }
             }
+          }
         }
         if (has && proposed == 0) {  // ended before the evaluation (xtest / gtest)
             io.store(ln, st, fit);
@@ -1775,7 +1914,14 @@ DPH_HD void run_stage(const Lanes<G>& ln, PixelState<Mo::NE>& px, const Options&
         if (Stage::kStash) st.template stash_get<stash_floats(G, Mo::kStoreE)>(px.stash, p);
         if (pass) {
             bool accepted;
+            float xold_lam[P + 1];
+            if (Stage::kTie && opt.exact_ties) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) xold_lam[i] = st.x[i];
+                xold_lam[P] = st.lam_of_step();
+            }
             const bool done = st.consume(opt, nrm, p, q1, accepted);
+            if (Stage::kTie && opt.exact_ties && accepted && !init) st.note_accepted(xold_lam, px.y + px.stride);
             if (accepted) px.cur = 1 - px.cur;
             if (accepted || init) old_irregular = trial_irregular;  // the first pass evaluates the accepted point itself
             if (done) {

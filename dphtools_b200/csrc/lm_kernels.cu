@@ -122,18 +122,20 @@ int validate(const dphlm_desc* d) {
 }
 
 // `ws` (optional): caller-provided device workspace of at least workspace_bytes(d)
-int park_capacity(long long n) {
-    long long c = n / 16;
+// capacity of each straggler list.  With DPHLM_FLAG_EXACT_TIES up to a third of the fits pass through the lm() list
+// (lm_core.cuh: tie_break), hence n / 2 there.
+int park_capacity(long long n, bool exact) {
+    long long c = exact ? n / 2 : n / 16;
     if (c < 256) c = 256;
-    if (c > 65536) c = 65536;
+    if (c > (exact ? 8388608 : 65536)) c = exact ? 8388608 : 65536;
     return (int)c;
 }
-size_t park_ready_bytes(long long n) { return ((3 * (size_t)park_capacity(n) * sizeof(int)) + 255) & ~size_t(255); }
-size_t park_bytes(long long n) {  // header (sync words + work counters), three ready arrays, three record arrays
-    return 256 + park_ready_bytes(n) + 3 * (size_t)park_capacity(n) * kParkRecord * sizeof(float);
+size_t park_ready_bytes(long long n, bool exact) { return ((3 * (size_t)park_capacity(n, exact) * sizeof(int)) + 255) & ~size_t(255); }
+size_t park_bytes(long long n, bool exact) {  // header (sync words + work counters), three ready arrays, three record arrays
+    return 256 + park_ready_bytes(n, exact) + 3 * (size_t)park_capacity(n, exact) * kParkRecord * sizeof(float);
 }
 size_t workspace_bytes(const dphlm_desc* d) {
-    return (((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255)) + park_bytes(d->n_fits) +
+    return (((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255)) + park_bytes(d->n_fits, d->flags & DPHLM_FLAG_EXACT_TIES) +
            (d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float));
 }
 
@@ -189,7 +191,7 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     a.popt = d->popt; a.info = d->info; a.nfev = d->nfev; a.chisq = d->chisq;
     a.p_ls = d->p_ls; a.counts = d->counts; a.x_acc = d->x_acc;
     a.n_fits = d->n_fits; a.h = d->dim0; a.w = d->dim1;
-    a.opt = Options{d->ftol, d->xtol, d->gtol, d->factor, d->maxfev};
+    a.opt = Options{d->ftol, d->xtol, d->gtol, d->factor, d->maxfev, (d->flags & DPHLM_FLAG_EXACT_TIES) ? 1 : 0};
     if (d->flags & DPHLM_FLAG_TIMING) {
         for (auto& e : g_timing.ev)
             if (!e) CUDA_TRY(cudaEventCreate(&e));
@@ -199,7 +201,8 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     const int G = d->group_lanes ? d->group_lanes : auto_group(a.h * a.w, d->model, d->n_fits, d->flags & DPHLM_FLAG_PIPELINED);
     // workspace: pre-fit exit codes, and the pre-fit parameters when the caller does not want them
     const size_t b_ier = ((size_t)d->n_fits * sizeof(int) + 255) & ~size_t(255);
-    const size_t b_park = park_bytes(d->n_fits);
+    const bool exact = d->flags & DPHLM_FLAG_EXACT_TIES;
+    const size_t b_park = park_bytes(d->n_fits, exact);
     const size_t b_pls = d->p_ls ? 0 : (size_t)d->n_fits * d->n_param * sizeof(float);
     const bool u16 = (d->flags & DPHLM_FLAG_DATA_U16) && !ws_in;  // the host path widens into its own slot buffer
     const size_t b_wide = u16 ? (size_t)d->n_fits * a.h * a.w * sizeof(float) : 0;
@@ -215,17 +218,17 @@ int fit_device(const dphlm_desc* d, DeviceCtx* ctx, cudaStream_t s, char* ws_in 
     // 256-byte header (sync words, then the work counters of the two main kernels at byte 64) and the straggler
     // lists; DPHLM_FLAG_NO_HANDOFF keeps every fit in the group that started it
     ParkLists pl{};
-    pl.cap = (d->flags & DPHLM_FLAG_NO_HANDOFF) ? 0 : park_capacity(d->n_fits);
+    pl.cap = (d->flags & DPHLM_FLAG_NO_HANDOFF) ? 0 : park_capacity(d->n_fits, exact);
     pl.sync = reinterpret_cast<int*>(ws + b_ier);
     a.counter = reinterpret_cast<unsigned long long*>(ws + b_ier + 64);
     pl.ready = reinterpret_cast<int*>(ws + b_ier + 256);
-    pl.rec = reinterpret_cast<float*>(ws + b_ier + 256 + park_ready_bytes(d->n_fits));
+    pl.rec = reinterpret_cast<float*>(ws + b_ier + 256 + park_ready_bytes(d->n_fits, exact));
     // the pre-fit results start as "not published yet" (exit code 0, parameters NaN) for an lm() kernel that starts early
     const bool skip = d->flags & DPHLM_FLAG_SKIP_PREFIT;
     a.skip_prefit = skip ? 1 : 0;
     if (skip) a.p_ls = const_cast<float*>(d->p0);  // lm() alone starts from p0 (nothing writes p_ls then)
     {
-        const long long n_zero = (long long)((256 + (pl.cap ? park_ready_bytes(d->n_fits) : 0)) / sizeof(int));
+        const long long n_zero = (long long)((256 + (pl.cap ? park_ready_bytes(d->n_fits, exact) : 0)) / sizeof(int));
         const long long n_pls = skip ? 0 : d->n_fits * d->n_param;
         long long blocks = (std::max<long long>(d->n_fits, n_pls) + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
@@ -377,7 +380,7 @@ static int host_enqueue(const dphlm_desc* d, int device) {
     for (size_t i = 1; i < bounds.size(); ++i) chunk = std::max(chunk, bounds[i] - bounds[i - 1]);
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
                  b_cnt = align_up(chunk * 16), b_x = align_up(M * 4) + 256;  // xaxis + model constants
-    const size_t b_ws = align_up(chunk * 4) + align_up(park_bytes(chunk)) + align_up(chunk * P * 4);
+    const size_t b_ws = align_up(chunk * 4) + align_up(park_bytes(chunk, d->flags & DPHLM_FLAG_EXACT_TIES)) + align_up(chunk * P * 4);
     const bool u16 = d->flags & DPHLM_FLAG_DATA_U16;
     const size_t b_raw = u16 ? align_up(chunk * M * 2) : 0;
     const size_t need = b_data + b_raw + 4 * b_par + 3 * b_i + b_cnt + b_x + b_ws;

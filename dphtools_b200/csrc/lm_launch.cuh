@@ -33,7 +33,7 @@
 
 namespace dphlm {
 
-constexpr int kParkRecord = 32;  // floats per continuation record (>= 3 P + 6 for P <= 7)
+constexpr int kParkRecord = 40;  // floats per continuation record (>= 4 P + 9 for P <= 7)
 
 int fail(const std::string& m);  // sets the thread-local error text, returns -1
 #define CUDA_TRY(x)                                                                                    \
@@ -158,6 +158,22 @@ struct IoDevice {
         return __shfl_sync(ln.gmask, ok, src) != 0;
     }
 
+    // hand a fit whose xtol test is too close to call in float32 to the poller kernel (Options::exact_ties); no backlog limit:
+    // the pollers are sized for it (launch())
+    template <class St> __device__ bool park_tie(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const St& st, long long fit) const {
+        if (RESUME || a.produce.cap <= 0) return false;
+        const int src = __ffs(ln.gmask) - 1;
+        int ok = 0;
+        if (ln.lane == 0) {
+            float r[kParkRecord];
+            st.save(r);
+#pragma unroll
+            for (int k = 0; k <= Mo::P; ++k) r[St::kKeepAt + k] = px.y[px.stride + k];
+            ok = publish(a.produce, r, St::kRecord, fit) ? 1 : 0;
+        }
+        return __shfl_sync(ln.gmask, ok, src) != 0;
+    }
+
     // Claim the next fit index for this group and start copying its inputs.  `after` is the index of the fit the group is
     // about to work on (-1: none).  Near the end of the batch nothing is claimed ahead: a fit staged behind a long-running one
     // would be stuck there while other groups have already run out of work, so the last wave is handed out on demand
@@ -189,7 +205,8 @@ struct IoDevice {
     __device__ bool fetch_parked(const Lanes<G>& ln, PixelState<Mo::NE>& px, Stage& st, long long& fit) const {
         constexpr int P = Mo::P;
         const long long t0 = clock64();
-        int q = -1, slot = 0;
+        int q = -1, slot = 0, r = 0;
+        for (;;) {  // until a published record has been claimed
         for (;;) {
             // all lanes run the same loop; lane 0 decides
             int claim = -1, got = 0, finished = 0;
@@ -200,7 +217,13 @@ struct IoDevice {
                     const int c = *reinterpret_cast<volatile int*>(pq.cons);
                     int n = *reinterpret_cast<volatile int*>(pq.count);
                     if (n > pq.cap) n = pq.cap;
-                    if (c < n && atomicCAS(pq.cons, c, c + 1) == c) { claim = k; got = c; }
+                    // a ticket, not a compare-and-swap: with hundreds of warps on one list (DPHLM_FLAG_EXACT_TIES) the losers of a
+                    // CAS round sleep and the list drains at one fit per microsecond.  A ticket beyond the current count (two warps
+                    // saw the same last entry) is waited for below like any other slot, and given up when the producers have gone
+                    if (c < n) {
+                        const int t = atomicAdd(pq.cons, 1);
+                        if (t < pq.cap) { claim = k; got = t; }
+                    }
                 }
                 if (claim < 0) {
                     bool done = true;
@@ -231,15 +254,39 @@ struct IoDevice {
             if (finished) return false;
             __nanosleep(2000);
         }
-        const ParkQueue& pq = a.consume[q];
-        int r = 0;
-        while ((r = *reinterpret_cast<volatile int*>(pq.ready + slot)) == 0) {  // the record is being written
-            if (clock64() - t0 > kPollTimeoutCycles) {
-                if (a.error_flag && ln.lane == 0) *reinterpret_cast<volatile int*>(a.error_flag) = 1;
-                return false;
+        // wait for the record of the claimed slot (lane 0 polls, all lanes follow): 1 = there, 2 = it will never come (the
+        // ticket is beyond what the producers published before they left), 3 = watchdog
+        int state = 0;
+        if (ln.lane == 0) {
+            const ParkQueue& pq = a.consume[q];
+            while (state == 0) {
+                r = *reinterpret_cast<volatile int*>(pq.ready + slot);
+                if (r != 0) { state = 1; break; }
+                bool gone = true;
+                for (int k = 0; k < 2; ++k)
+                    if (a.wait_done[k] && *reinterpret_cast<volatile int*>(a.wait_done[k]) == 0) gone = false;
+                if (gone) {
+                    __threadfence();
+                    int n = *reinterpret_cast<volatile int*>(pq.count);
+                    if (n > pq.cap) n = pq.cap;
+                    r = *reinterpret_cast<volatile int*>(pq.ready + slot);
+                    if (r != 0) { state = 1; break; }
+                    if (slot >= n) { state = 2; break; }
+                }
+                if (clock64() - t0 > kPollTimeoutCycles) {
+                    if (a.error_flag) *reinterpret_cast<volatile int*>(a.error_flag) = 1;
+                    state = 3;
+                    break;
+                }
+                __nanosleep(200);
             }
-            __nanosleep(200);
         }
+        state = __shfl_sync(ln.gmask, state, 0);
+        r = __shfl_sync(ln.gmask, r, 0);
+        if (state == 3) return false;
+        if (state == 1) break;
+        }
+        const ParkQueue& pq = a.consume[q];
         __threadfence();
         const long long idx = r - 1;
         const float* d = a.data + idx * px.M;
@@ -258,6 +305,10 @@ struct IoDevice {
 #pragma unroll
             for (int k = 0; k < Stage::kRecord; ++k) rec[k] = src[k];
             st.resume(rec, a.consts);
+            if constexpr (Stage::kTie) {  // the previous accepted point goes back behind the working ROI (StageB::note_accepted)
+                if (ln.lane <= Mo::P) px.y[px.stride + ln.lane] = rec[Stage::kKeepAt + ln.lane];
+                __syncwarp(ln.gmask);
+            }
         }
         fit = idx;
         return true;
@@ -371,7 +422,7 @@ struct IoDevice {
         a.info[fit] = st.info;
         a.nfev[fit] = st.ev;
         a.chisq[fit] = st.chisq_ret;
-        if (a.counts) { a.counts[4 * fit + 1] = st.n_acc; a.counts[4 * fit + 2] = st.n_rej; a.counts[4 * fit + 3] = 0; }
+        if (a.counts) { a.counts[4 * fit + 1] = st.n_acc; a.counts[4 * fit + 2] = st.n_rej; a.counts[4 * fit + 3] = st.n_tie; }
         if (a.x_acc) {
 #pragma unroll
             for (int k = 0; k < Mo::P; ++k) a.x_acc[fit * Mo::P + k] = st.x[k];
@@ -679,6 +730,11 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     const size_t smem_w = sizeof(float) * (2 * (size_t)((M + 1) & ~1) + (size_t)kWarps * group_region(padded_stride(M, 32), Mo::kStoreE ? Mo::NE : 0, Mo::table_floats(a0.h, a0.w), 32));
     const bool handoff = G < 32 && pl.cap > 0;
     const int kPollerCtas = budget_from_env("DPHLM_POLLER_CTAS", kPollerCtasDefault);  // tuning aid
+    // With Options::exact_ties 3-20 % of the fits pass through the lm() poller (it re-decides the borderline xtol tests in
+    // float64, lm_core.cuh: tie_break): a whole-machine launch BEHIND the lm() main kernel then, instead of eight CTAs beside it
+    // (one warp per fit is latency-bound: it takes the width of the machine to get through tens of thousands of them).
+    const bool exact = a0.opt.exact_ties != 0;
+    const int kPollerCtasB = exact ? 0 : kPollerCtas;
     using SA = StageA<Mo>;
     using SB = StageB<Mo, MLE>;
     unsigned long long* const counters = a0.counter;  // work counters of the two main kernels
@@ -720,7 +776,7 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     CUDA_TRY(cudaStreamWaitEvent(sd.stream_b, sd.fork_ev, 0));
     int rc = 0;
     if (!skip_prefit) {
-        rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream, 2 * kPollerCtas);
+        rc = launch_stage(dphlm_stage_kernel<SA, Mo, G, IoDevice<SA, Mo, G, false, false, false>>, a, FPW, smem, ctx, stream, kPollerCtas + kPollerCtasB);
         if (rc) return rc;
         rc = launch_stage(dphlm_stage_kernel<SA, Mo, 32, IoDevice<SA, Mo, 32, false, false, true>>, aw, 1, smem_w, ctx, sd.stream_a, 0, kPollerCtas);
         if (rc) return rc;
@@ -737,18 +793,25 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     bw.consume[0] = pl.queue(1); bw.consume[1] = skip_prefit ? none : pl.queue(2);
     bw.wait_done[0] = pl.sync + kSyncDoneBMain; bw.wait_done[1] = skip_prefit ? nullptr : pl.sync + kSyncDoneAWide;
     bw.exit_counter = bw.done_flag = nullptr;
+    if (exact) b.max_backlog = pl.cap;  // nobody takes fits off the list while the main kernel runs: no limit on what waits there
     // The lm() kernel directly follows the pre-fit kernel in the stream and may start in the CTA slots that one frees while its
     // last fits finish: it waits per fit for the pre-fit's exit code (IoDevice::fetch), not for the grid.  Timing events
     // between the two launches would serialise them, so a timed call keeps the plain stream order.
     const bool early = !a.ev && !skip_prefit && !getenv("DPHLM_NO_EARLY_START");
-    rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream, 2 * kPollerCtas, 0, early);
+    rc = launch_stage(dphlm_stage_kernel<SB, Mo, G, IoDevice<SB, Mo, G, true, MLE, false>>, b, FPW, smem, ctx, stream, kPollerCtas + kPollerCtasB, 0, early);
     if (rc) return rc;
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[2], stream));  // end of the lm() main kernel itself
-    rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, bw, 1, smem_w, ctx, sd.stream_b, 0, kPollerCtas);
-    if (rc) return rc;
-    CUDA_TRY(cudaEventRecord(sd.join_b, sd.stream_b));
-    if (!skip_prefit) CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_a, 0));
-    CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_b, 0));
+    if (exact) {  // after the main kernel and the pre-fit poller (which feeds it the late pre-fits), on the caller's stream
+        if (!skip_prefit) CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_a, 0));
+        rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, bw, 1, smem_w, ctx, stream);
+        if (rc) return rc;
+    } else {
+        rc = launch_stage(dphlm_stage_kernel<SB, Mo, 32, IoDevice<SB, Mo, 32, true, MLE, true>>, bw, 1, smem_w, ctx, sd.stream_b, 0, kPollerCtasB);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(sd.join_b, sd.stream_b));
+        if (!skip_prefit) CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_a, 0));
+        CUDA_TRY(cudaStreamWaitEvent(stream, sd.join_b, 0));
+    }
     if (a.ev) CUDA_TRY(cudaEventRecord(a.ev[3], stream));  // the pollers have finished the stragglers
     return 0;
 }

@@ -98,7 +98,7 @@ def _check(rc):
 
 def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xtol=XTOL, gtol=0.0, maxfev=None,
                     factor=100.0, return_stage1=False, return_counts=False, group_lanes=0, device=None, timing=False, out=None,
-                    return_pcov=None, return_x_acc=False, pipelined=False, skip_prefit=False, wait=True):
+                    return_pcov=None, return_x_acc=False, pipelined=False, skip_prefit=False, wait=True, exact_ties=False):
     """Fit ``N`` independent ROIs / histograms: the batched form of per-ROI
     ``curve_fit(model, xdata, roi.ravel(), p0, jac=model.jac, method=method)`` (``lm.py:510-685``).
 
@@ -122,6 +122,9 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     wait : host path only: ``False`` returns as soon as the copies and kernels are enqueued (``dphlm_fit_batch_host_async``; use
         :func:`pinned_empty` buffers and leave them alone until :func:`host_wait`), so that the next batch's upload overlaps
         this batch's kernels.
+    exact_ties : re-decide in float64 the ``lm()`` trips whose step is within a factor 64 of the ``xtol`` threshold
+        (``DPHLM_FLAG_EXACT_TIES``): the fits that end that close -- 0.1 to 2 % of a batch -- then get the reference's
+        ``info`` (1 or 2) instead of a coin flip; a few per cent slower.
     skip_prefit : start the ``lm()`` loop directly at ``p0`` (``DPHLM_FLAG_SKIP_PREFIT``): the reference's ``lm()`` rather
         than its ``curve_fit`` (``lm.py:221-236``).
     out : host path only: a ``BatchResult`` of preallocated C-contiguous arrays to write into (use
@@ -138,7 +141,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
     if _is_torch(data) and data.is_cuda:
         want_acc = return_x_acc or return_pcov == "jtj"
         res = _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1,
-                          return_counts, group_lanes, timing, want_acc, pipelined, skip_prefit)
+                          return_counts, group_lanes, timing, want_acc, pipelined, skip_prefit, exact_ties)
         if return_pcov:
             if pipelined:
                 raise ValueError("return_pcov needs the results: call covariance() after join()")
@@ -196,7 +199,7 @@ def curve_fit_batch(model, data, p0, method="mle", xdata=None, *, ftol=FTOL, xto
         d.p_ls = out.p_ls[lo:hi].ctypes.data if return_stage1 else None
         d.counts = out.counts[lo:hi].ctypes.data if return_counts else None
         d.x_acc = out.x_acc[lo:hi].ctypes.data if out.x_acc is not None else None
-        d.flags = (_lib.FLAG_DATA_U16 if u16 else 0) | (_lib.FLAG_SKIP_PREFIT if skip_prefit else 0)
+        d.flags = (_lib.FLAG_DATA_U16 if u16 else 0) | (_lib.FLAG_SKIP_PREFIT if skip_prefit else 0) | (_lib.FLAG_EXACT_TIES if exact_ties else 0)
         if not wait:
             _host_pending.setdefault(dev, []).append((data, p0, xa, consts, out))  # keep the buffers alive until host_wait()
             return _lib.lib().dphlm_fit_batch_host_async(ctypes.byref(d), dev)
@@ -290,7 +293,7 @@ def pinned_empty(shape, dtype=np.float32):
 
 
 def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev, factor, return_stage1, return_counts, group_lanes,
-                timing=False, return_x_acc=False, pipelined=False, skip_prefit=False):
+                timing=False, return_x_acc=False, pipelined=False, skip_prefit=False, exact_ties=False):
     import torch
 
     if data.dtype != torch.float32 or not data.is_contiguous():
@@ -324,7 +327,8 @@ def _fit_device(model, data, p0, method, xdata, one_d, ftol, xtol, gtol, maxfev,
     d.p_ls = p_ls.data_ptr() if return_stage1 else None
     d.counts = counts.data_ptr() if return_counts else None
     d.x_acc = x_acc.data_ptr() if return_x_acc else None
-    d.flags = (_lib.FLAG_TIMING if timing else 0) | (_lib.FLAG_PIPELINED if pipelined else 0) | (_lib.FLAG_SKIP_PREFIT if skip_prefit else 0)
+    d.flags = ((_lib.FLAG_TIMING if timing else 0) | (_lib.FLAG_PIPELINED if pipelined else 0) | (_lib.FLAG_SKIP_PREFIT if skip_prefit else 0)
+               | (_lib.FLAG_EXACT_TIES if exact_ties else 0))
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _check(_lib.lib().dphlm_fit_batch(ctypes.byref(d), ctypes.c_void_p(stream)))

@@ -30,7 +30,7 @@ def lib():
     return _lib
 
 
-def fit_batch(model_id, method, data, p0, xaxis=None, ftol=1.49012e-8, xtol=1.49012e-8, gtol=0.0, factor=100.0, maxfev=0, budget=0, consts=None, skip_prefit=False):
+def fit_batch(model_id, method, data, p0, xaxis=None, ftol=1.49012e-8, xtol=1.49012e-8, gtol=0.0, factor=100.0, maxfev=0, budget=0, consts=None, skip_prefit=False, exact_ties=False):
     data = np.ascontiguousarray(data, dtype=np.float32)
     p0 = np.ascontiguousarray(p0, dtype=np.float32)
     n, npar = p0.shape
@@ -49,7 +49,7 @@ def fit_batch(model_id, method, data, p0, xaxis=None, ftol=1.49012e-8, xtol=1.49
         ctypes.c_int(model_id), ctypes.c_int(1 if method == "mle" else 0), ctypes.c_int(npar), ctypes.c_int(h), ctypes.c_int(w),
         ctypes.c_long(n), ptr(data), ptr(xa) if xa is not None else None, ptr(p0), ctypes.c_float(ftol), ctypes.c_float(xtol),
         ctypes.c_float(gtol), ctypes.c_float(factor), ctypes.c_int(maxfev), ctypes.c_int(budget), ptr(out["popt"]), ptr(out["p_ls"]), ptr(out["info"]),
-        ptr(out["nfev"]), ptr(out["chisq"]), ptr(out["counts"]), ptr(cs) if cs is not None else None, ctypes.c_int(1 if skip_prefit else 0),
+        ptr(out["nfev"]), ptr(out["chisq"]), ptr(out["counts"]), ptr(cs) if cs is not None else None, ctypes.c_int(1 if skip_prefit else 0), ctypes.c_int(1 if exact_ties else 0),
     )
     if rc != 0:
         raise ValueError("unsupported model/n_param")

@@ -116,7 +116,7 @@ struct HostIoMain {
     void store(const Lanes<1>&, const StageB<Mo, MLE>& st, long long fit) {
         for (int k = 0; k < Mo::P; ++k) b.popt[fit * Mo::P + k] = st.xret[k];
         b.info[fit] = st.info; b.nfev[fit] = st.ev; b.chisq[fit] = st.chisq_ret;
-        b.counts[4 * fit + 1] = st.n_acc; b.counts[4 * fit + 2] = st.n_rej; b.counts[4 * fit + 3] = 0;
+        b.counts[4 * fit + 1] = st.n_acc; b.counts[4 * fit + 2] = st.n_rej; b.counts[4 * fit + 3] = st.n_tie;
     }
 };
 
@@ -157,8 +157,8 @@ static void run(int h, int w, const float* xaxis, const Options& opt, Buffers& b
 extern "C" int emu_fit_batch(int model, int method, int n_param, int h, int w, long n, const float* data,
                              const float* xaxis, const float* p0, float ftol, float xtol, float gtol, float factor,
                              int maxfev, int budget, float* popt, float* p_ls, int* info, int* nfev, float* chisq, int* counts,
-                             const float* consts, int skip_prefit) {
-    Options opt{ftol, xtol, gtol, factor, maxfev};
+                             const float* consts, int skip_prefit, int exact_ties) {
+    Options opt{ftol, xtol, gtol, factor, maxfev, exact_ties};
     Buffers b{h * w, n, data, p0, popt, p_ls, chisq, info, nfev, counts, std::vector<int>(n, 0), budget, {}, std::vector<char>(n, 0), consts, skip_prefit};
 #define RUN(...)                                                 \
     do {                                                         \

@@ -26,7 +26,7 @@ dp = [torch.from_numpy(s["p0"]).cuda() for s in sets]
 
 
 def step(i, **kw):
-    return dph.curve_fit_batch(model, dd[i % 4], dp[i % 4], method, xa, group_lanes=lanes, **kw)
+    return dph.curve_fit_batch(model, dd[i % 4], dp[i % 4], method, xa, group_lanes=lanes, exact_ties=bool(os.environ.get("EXACT_TIES")), **kw)
 
 
 t0 = time.perf_counter()

@@ -201,3 +201,19 @@ def test_device_guess_is_the_reference_recipe_and_the_batch_driver_runs_on_the_g
         want, _ = fitfuncs.multi_exp_fit(dirty[i].astype(float), t, components=2, method="mle")
         np.testing.assert_allclose(res.popt[i], want, rtol=1e-5)
         np.testing.assert_allclose(res.popt[i], clean.popt[i].cpu().numpy(), rtol=0.2)  # one bin fewer: nearly the same fit
+
+
+@pytest.mark.parametrize("name", ["c2_mle", "c3_mle", "c5_mle", "c6_mle", "c7_mle", "c9_mle", "c4_mle", "c8_mle"])
+def test_exact_ties_give_the_reference_flag_on_gpu(golden, name):
+    """DPHLM_FLAG_EXACT_TIES: identical info on >= 99.9 % of every golden set (north_star "identical convergence flags",
+    SURVEY 7.3), device and host entry."""
+    g = golden(name)
+    model = models.resolve(g["model"], g["consts"])
+    r = dph.curve_fit_batch(model, torch.from_numpy(g["data"]).cuda(), torch.from_numpy(g["p0"]).cuda(), g["method"], g["xaxis"],
+                            exact_ties=True)
+    out = dict(popt=r.popt.cpu().numpy(), info=r.info.cpu().numpy(), nfev=r.nfev.cpu().numpy())
+    rep = parity_report(g["model"], out, g)
+    print(name, rep)
+    assert rep["converged_equal"] == 1.0 and rep["info_equal"] >= 0.999 and rep["within_rtol"] >= 0.9999, rep
+    h = dph.curve_fit_batch(model, g["data"][:512], g["p0"][:512], g["method"], g["xaxis"], exact_ties=True)
+    np.testing.assert_array_equal(h.info, out["info"][:512])
