@@ -271,7 +271,7 @@ def main():
         return reps, last
 
     # `value`: the K steps issued as pipelined calls (DPHLM_FLAG_PIPELINED: each call is complete work on its own buffers; the
-    # library keeps two in flight on its own streams, so the drain and the stragglers of one step run under the next) and
+    # library keeps three in flight on its own streams, so the drain and the stragglers of one step run under the next) and
     # joined before the closing event.  `serialized` below is the same with every call stream-ordered behind the previous one.
     sampler.active = True
     repeats, res = timed_steps(True)
@@ -287,7 +287,7 @@ def main():
     for i in range(min(args.steps, 8)):
         torch.cuda.synchronize()
         r = dph.curve_fit_batch(models.gauss2d, d_data[i % N_SETS], d_p0[i % N_SETS], "mle", return_counts=True,
-                                group_lanes=args.group_lanes, timing=True)
+                                group_lanes=args.group_lanes or 2, timing=True)  # two lanes per fit: what a pipelined call of this size picks
         ms_pre, ms_main, ms_tail = _lib.last_kernel_ms()
         t_pre.append(ms_pre * 1e-3)
         t_main.append(ms_main * 1e-3)
@@ -310,8 +310,8 @@ def main():
     h_probe = torch.from_numpy(dph.pinned_empty(n * (ROI * ROI + 5)))  # the allocator the e2e leg uses (cudaHostAlloc)
     h_probe.zero_()
     d_probe = torch.empty_like(h_probe, device=dev)
-    probe_streams = [torch.cuda.Stream(device=dev) for _ in range(4)]  # four copies in flight, like the host entry's chunks
-    quarter = h_probe.numel() // 4
+    probe_streams = [torch.cuda.Stream(device=dev) for _ in range(8)]  # eight copies in flight, like the host entry's staging slots
+    quarter = h_probe.numel() // 8
 
     def probe_round():
         for k, st_ in enumerate(probe_streams):
@@ -320,18 +320,21 @@ def main():
 
     for _ in range(2):
         probe_round()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for st_ in probe_streams:
-        st_.wait_event(ev0)
-    for _ in range(8):
-        probe_round()
-    for st_ in probe_streams:
-        torch.cuda.current_stream().wait_stream(st_)
-    ev1.record()
-    barrier()
-    h2d_gbs = torch.tensor([8 * 4 * quarter * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9], device=dev)
+    best_gbs = 0.0
+    for _ in range(3):  # best of three blocks of eight rounds
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for st_ in probe_streams:
+            st_.wait_event(ev0)
+        for _ in range(8):
+            probe_round()
+        for st_ in probe_streams:
+            torch.cuda.current_stream().wait_stream(st_)
+        ev1.record()
+        barrier()
+        best_gbs = max(best_gbs, 8 * 8 * quarter * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
+    h2d_gbs = torch.tensor([best_gbs], device=dev)
     if world > 1:
         dist.all_reduce(h2d_gbs, op=dist.ReduceOp.MIN)
     h2d_gbs = float(h2d_gbs.item())
@@ -415,7 +418,7 @@ def main():
             "config": {
                 "workload": "1e5 symmetric 2D Gaussian MLE fits per GPU and step, 11x11 ROIs, photons 100-5000 (BASELINE configs[1])",
                 "fits_per_gpu_per_step": n, "sharding": "independent fits, contiguous shards, no collective",
-                "pipeline": "steps issued as pipelined calls (two in flight on the library's streams), joined before the closing event",
+                "pipeline": "steps issued as pipelined calls (three in flight on the library's streams), joined before the closing event",
                 "l2": "inputs rotate over %d distinct sets (%.0f MB) > 126 MB L2" % (N_SETS, N_SETS * n * ROI * ROI * 4 / 1e6),
                 "converged_fraction": float(((info >= 1) & (info <= 4)).mean()),
             },

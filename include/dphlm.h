@@ -84,7 +84,7 @@ typedef struct dphlm_desc {
 #define DPHLM_FLAG_DATA_U16 4
 /* flags (dphlm_fit_batch only): pipelined call.  The kernels are enqueued on one of the library's own streams behind everything
  * that is in `stream` at the time of the call, and `stream` does NOT wait for them: consecutive pipelined calls overlap
- * (two in flight; the tail of one call -- its last fits, its stragglers -- runs under the next call's kernels), which is
+ * (three in flight; the tail of one call -- its last fits, its stragglers -- runs under the next call's kernels), which is
  * worth ~25 % at 1e5 fits per call.  The caller must treat the outputs as pending, keep all buffers alive, and not feed
  * them to later work until dphlm_join(stream) has made `stream` wait for every pending pipelined call. */
 #define DPHLM_FLAG_PIPELINED 8

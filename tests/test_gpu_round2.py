@@ -17,7 +17,7 @@ torch = pytest.importorskip("torch")
 
 
 def test_pipelined_calls_equal_stream_ordered_calls(golden):
-    """DPHLM_FLAG_PIPELINED changes where the kernels run (the library's own streams, two calls in flight), not what they
+    """DPHLM_FLAG_PIPELINED changes where the kernels run (the library's own streams, three calls in flight), not what they
     compute: bit-identical results once join() has been called."""
     g = golden("c2_mle")
     data, p0 = torch.from_numpy(g["data"]).cuda(), torch.from_numpy(g["p0"]).cuda()
