@@ -167,12 +167,11 @@ DPH_HD T log1p_pos(T u) {
     return v_sel_small(u, kLog1pSmall, p, big);
 }
 
-// expm1(a) for |a| <= 1/16 (Taylor, degree 5, truncation < 2e-9 relative); callers handle larger |a| by
+// expm1(a) for |a| <= 1/16 (Taylor, degree 4, truncation a^4 / 120 < 1.3e-7 relative); callers handle larger |a| by
 // direct differences of the stored exponentials.
 template <class T>
 DPH_HD T expm1_small(T a) {
-    T p = T(1.0f / 120.0f);
-    p = f_fma(p, a, T(1.0f / 24.0f));
+    T p = T(1.0f / 24.0f);
     p = f_fma(p, a, T(1.0f / 6.0f));
     p = f_fma(p, a, T(0.5f));
     return f_fma(p * a, a, a);
@@ -184,24 +183,23 @@ constexpr float kSmallArg = 0.0625f;
 //   t(f0) - t(f1) = (y/f0 - 1) (f1 - f0) - y u^2 S(u),     S(u) = 1/2 - u/3 + u^2/4 - ...   (u - ln(1 + u) = u^2 S(u))
 // The first-order term uses the very residual 1 - y/f0 the gradient at the accepted point was summed from (same inputs, same
 // instructions), so first-order term and step stay consistent down to rounding: that, not the accuracy of the logarithm,
-// is what keeps the signs of reductions ~1e-9 of chi-square right.  The series is cut where its truncation stays below
-// what the lg2-based form delivers at the switch point |u| = 1/8 (u^7/7 = 7e-8 absolute); beyond it -- a step that changes
-// a pixel's model value by more than 12 % -- a rarely taken branch substitutes the logarithm.
+// is what keeps the signs of reductions ~1e-9 of chi-square right.  The series is cut at degree 3 (truncation u^4/6 of S: 8e-5 of the
+// second-order term at the switch point |u| = 1/8, on steps whose reduction is far above the tolerances); beyond the switch
+// point -- a step that changes a pixel's model value by more than 12 % -- a rarely taken branch substitutes the logarithm.
 constexpr float kSeriesMax = 0.125f;
+// -S(u): the sign is folded into the coefficients
 template <class T>
-DPH_HD T series_ln(T u) {  // S(u), degree 4
-    T p = T(1.0f / 6.0f);
-    p = f_fma(p, u, T(-0.2f));
-    p = f_fma(p, u, T(0.25f));
-    p = f_fma(p, u, T(-1.0f / 3.0f));
-    return f_fma(p, u, T(0.5f));
+DPH_HD T neg_series_ln(T u) {  // degree 3 (truncation u^4/6: below 1e-4 of the second-order term at the switch point)
+    T p = T(0.2f);
+    p = f_fma(p, u, T(-0.25f));
+    p = f_fma(p, u, T(1.0f / 3.0f));
+    return f_fma(p, u, T(-0.5f));
 }
 template <class T>
-DPH_HD T series_ln3(T u) {  // S(u), degree 3 (the predicted reduction is only compared with the actual one at the 1 % level)
-    T p = T(-0.2f);
-    p = f_fma(p, u, T(0.25f));
-    p = f_fma(p, u, T(-1.0f / 3.0f));
-    return f_fma(p, u, T(0.5f));
+DPH_HD T neg_series_ln_pred(T u) {  // degree 2 (the predicted reduction is only compared with the actual one at the 1 % level)
+    T p = T(-0.25f);
+    p = f_fma(p, u, T(1.0f / 3.0f));
+    return f_fma(p, u, T(-0.5f));
 }
 DPH_HD float v_absmax(float a, float b) { return fmaxf(fabsf(a), fabsf(b)); }
 DPH_HD float v_absmax(f2 a, f2 b) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))); }
@@ -303,7 +301,11 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     template <class L> DPH_HD static void fill_tables(const L&, const Par& q0, Par& q1, Step&, float*, int, int, int) {
         q1.ad1 = q1.x0 - q0.x0; q1.ad2 = q1.y0 - q0.y0; q1.anh = q0.nh;
     }
-    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, T* e) {
+    // The accepted point's exponential, from the REALISED step (ad1 = x0_new - x0_old is exact in float32, so dxa is cx - x0_old
+    // to one rounding).  Not from the r2_old that diff() forms out of the nominal step: x0 + d rounds, the two differ by up to
+    // half an ulp of x0, and that much inconsistency between this value and the one the gradient of the accepted point was
+    // summed from is enough to lose the last trips (tried: nfev equality 95 % -> 77 %, 0.2 % of the fits no longer converge).
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, const Diff<T>&, T* e) {
         const T dxa = g.dx + T(q.ad1), dya = g.dy + T(q.ad2);
         e[0] = v_ex2(f_fma(dxa, dxa, dya * dya) * T(q.anh));
     }
@@ -321,9 +323,20 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     }
     template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) { e[0] = v_ex2(g.r2 * T(q.nh)); }
     template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
-    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
-        T t = e[0] * T(q.as2);
-        J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = e[0] * T(q.as3) * g.r2; J[4] = T(1.0f);
+    // Jacobian row WITHOUT the per-fit factors of its columns (amp/sigma^2, amp/sigma^2, amp/sigma^3): they are the same for
+    // every pixel, so the sums A = J^T W J and g = J^T r are formed from (e, e dx, e dy, e r2, 1) and scaled once per pass
+    // (post_scale), which takes two multiplications out of every pixel
+    template <class T> DPH_HD static void jac(const Par&, const Geo<T>& g, const T* e, T* J) {
+        J[0] = e[0]; J[1] = e[0] * g.dx; J[2] = e[0] * g.dy; J[3] = e[0] * g.r2; J[4] = T(1.0f);
+    }
+    DPH_HD static void post_scale(const Par& q, float* A, float* g) {
+        const float s[P] = {1.0f, q.as2, q.as2, q.as3, 1.0f};
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+#pragma unroll
+            for (int j = i; j < P; ++j) A[i * P - (i * (i - 1)) / 2 + (j - i)] *= s[i] * s[j];
+            g[i] *= s[i];
+        }
     }
     // float64 model value and Jacobian row at one pixel (the tie-break pass of StageB, see precise_normal; the covariance kernel)
     DPH_HD static void eval64(const double* p, const float*, double cx, double cy, double& f, double* J) {
@@ -386,9 +399,17 @@ struct Gauss2DFixed {
     }
     template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) { e[0] = v_ex2(g.r2 * T(q.nh)); }
     template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
-    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
-        T t = e[0] * T(q.as2);
-        J[0] = e[0]; J[1] = t * g.dx; J[2] = t * g.dy; J[3] = T(1.0f);
+    template <class T> DPH_HD static void jac(const Par&, const Geo<T>& g, const T* e, T* J) {  // unscaled columns, see Gauss2D::jac
+        J[0] = e[0]; J[1] = e[0] * g.dx; J[2] = e[0] * g.dy; J[3] = T(1.0f);
+    }
+    DPH_HD static void post_scale(const Par& q, float* A, float* g) {
+        const float s[P] = {1.0f, q.as2, q.as2, 1.0f};
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+#pragma unroll
+            for (int j = i; j < P; ++j) A[i * P - (i * (i - 1)) / 2 + (j - i)] *= s[i] * s[j];
+            g[i] *= s[i];
+        }
     }
     DPH_HD static void eval64(const double* p, const float* consts, double cx, double cy, double& f, double* J) {
         const double sig = consts ? double(consts[0]) : 1.0;
@@ -459,6 +480,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         J[5] = ae * g.u * g.v * T(q.ay - q.ax);
         J[6] = T(1.0f);
     }
+    DPH_HD static void post_scale(const Par&, float*, float*) {}
     DPH_HD static void eval64(const double* p, const float*, double cx, double cy, double& f, double* J) {
         const double c = cos(p[5]), s = sin(p[5]), dx = cx - p[1], dy = cy - p[2];
         const double u = c * dx + s * dy, v = -s * dx + c * dy, ax = 1.0 / (p[3] * p[3]), ay = 1.0 / (p[4] * p[4]);
@@ -607,7 +629,7 @@ struct Gauss2DIntegratedT {
         g.exa = cb.a; g.ux = cb.b; g.eya = rb.a; g.uy = rb.b;
     }
     template <class T> DPH_HD static void expo(const Par&, const Geo<T>& g, T* e) { e[0] = g.ex * g.ey; }
-    template <class T> DPH_HD static void expo_old(const Par&, const Geo<T>& g, T* e) { e[0] = g.exa * g.eya; }  // at the accepted point
+    template <class T> DPH_HD static void expo_old(const Par&, const Geo<T>& g, const Diff<T>&, T* e) { e[0] = g.exa * g.eya; }  // at the accepted point
     template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
     template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
         J[0] = e[0];
@@ -616,6 +638,7 @@ struct Gauss2DIntegratedT {
         if (!FIXED) J[3] = f_fma(g.sex, g.ey, g.ex * g.sey) * T(q.amp);
         J[kOff] = T(1.0f);
     }
+    DPH_HD static void post_scale(const Par&, float*, float*) {}
     DPH_HD static void axis64(double t, double sig, double& e, double& de, double& se) {
         const double a = 0.70710678118654752440 / sig, c = 0.39894228040143267794 / sig;
         const double tp = t + 0.5, tm = t - 0.5, zp = tp * a, zm = tm * a;
@@ -691,6 +714,7 @@ struct MultiExp {
         for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[i]; J[2 * i + 1] = g.x * e[i] * T(-q.a[i]); }
         if (OFFSET) J[2 * NEXP] = T(1.0f);
     }
+    DPH_HD static void post_scale(const Par&, float*, float*) {}
     DPH_HD static void eval64(const double* p, const float*, double cx, double, double& f, double* J) {
         f = OFFSET ? p[2 * NEXP] : 0.0;
 #pragma unroll
@@ -824,7 +848,7 @@ struct MultiExpIrf {
         }
     }
     template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) { conv(q.tbl, q.k, g, e); }
-    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, T* e) { conv(q.tbla, q.ka, g, e); }  // accepted point
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, const Diff<T>&, T* e) { conv(q.tbla, q.ka, g, e); }  // accepted point
     template <class T> DPH_HD static T value(const Par& q, const T* e) {
         T f = T(q.off);
 #pragma unroll
@@ -836,6 +860,7 @@ struct MultiExpIrf {
         for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[2 * i]; J[2 * i + 1] = e[2 * i + 1] * T(-q.a[i]); }
         if (OFFSET) J[2 * NEXP] = T(1.0f);
     }
+    DPH_HD static void post_scale(const Par&, float*, float*) {}
     // cy carries the bin index; consts = [W, m0, dt, irf...]
     DPH_HD static void eval64(const double* p, const float* consts, double, double cy, double& f, double* J) {
         f = OFFSET ? p[2 * NEXP] : 0.0;
@@ -1055,7 +1080,7 @@ DPH_HD void mle_weights(float f, float y, float& w, float& res) {
 
 // One pixel (T = float) or one pair of adjacent pixels (T = f2) of the regular, branch-free trial
 // evaluation: model at the trial point q1 = q0 + d, the chi-square reductions from per-pixel differences
-// (see series_ln) and, speculatively, the normal equations at the trial point.  QUIRK (lm.py:446-449): the
+// (see neg_series_ln) and, speculatively, the normal equations at the trial point.  QUIRK (lm.py:446-449): the
 // predicted model is f(x_new) + J(x_old) d.
 template <class Mo, bool MLE, bool PRED, class T>
 DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1, const typename Mo::Step& st, bool init,
@@ -1064,13 +1089,13 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
     typename Mo::template Diff<T> df;
     T e0[NE], J[P];
     Mo::expo(q1, g1, e1);
+    Mo::diff(q0, st, g1, df);
     if constexpr (Mo::kStoreE) {
 #pragma unroll
         for (int j = 0; j < NE; ++j) e0[j] = v_pick(init, e1[j], e0in[j]);
     } else {
-        Mo::expo_old(q1, g1, e0);  // on the first pass the tables of the accepted point equal the trial ones
+        Mo::expo_old(q1, g1, df, e0);  // on the first pass the accepted point is the trial point (zero step, equal tables)
     }
-    Mo::diff(q0, st, g1, df);
     const T f0 = Mo::value(q0, e0);
     const T f1 = Mo::value(q1, e1);
     const T dl = Mo::delta(q0, st, df, e0, e1);
@@ -1082,25 +1107,29 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
         const T f1c = v_max(f1, 0.0f);
         const T rf0 = v_rcp(f0);
         const T yf0 = y * rf0;
-        const T rn0 = yf0 - T(1.0f);  // -(1 - y/f0): minus the residual the gradient at the accepted point was summed from
+        const T rn0 = yf0 - T(1.0f);  // -(1 - y/f0): minus the residual the gradient at the accepted point was summed from 
+        // t(f0) - t(f1) = rn0 dl - (y/f0) dl u S(u)   (see neg_series_ln above).  The first-order term goes into the sum on its own,
+        // with the very rn0 (an exact product inside the multiply-add): folding it into one factor q = rn0 - (y/f0) u S(u) rounds
+        // q and costs 0.3 % of nfev equality on the golden sets; the second-order term follows as (y/f0 u dl) (-S(u)).
         const T u = dl * rf0;
-        T sa = (yf0 * dl) * u * series_ln(u);  // y (u - ln(1 + u))
+        const T yu = yf0 * u;
+        T sa = (yu * dl) * neg_series_ln(u);  // -y (u - ln(1 + u))
         if (PRED) {
             const T jd = Mo::jdx(q0, st, df, e0);
             const T dp = dl + jd;
             const T up = dp * rf0;
-            T sp = (yf0 * dp) * up * series_ln3(up);
+            T sp = ((yf0 * up) * dp) * neg_series_ln_pred(up);
             if (v_absmax(u, up) > kSeriesMax) {  // a step that changes this pixel by more than 12 %: rare
-                sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(-kLn2), u));
-                sp = v_sel_small(up, kSeriesMax, sp, y * f_fma(v_lg2(up + T(1.0f)), T(-kLn2), up));
+                sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(kLn2), T(0.0f) - u));
+                sp = v_sel_small(up, kSeriesMax, sp, y * f_fma(v_lg2(up + T(1.0f)), T(kLn2), T(0.0f) - up));
             }
             n.lo = v_min3(n.lo, f1c, f1c + jd);
-            n.predicted = f_fma(rn0, dp, n.predicted) - sp;
+            n.predicted = f_fma(rn0, dp, n.predicted) + sp;
         } else {
-            if (v_absmax(u) > kSeriesMax) sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(-kLn2), u));
+            if (v_absmax(u) > kSeriesMax) sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(kLn2), T(0.0f) - u));
             n.lo = v_min3(n.lo, f1c, f1c);
         }
-        n.actual = f_fma(rn0, dl, n.actual) - sa;
+        n.actual = f_fma(rn0, dl, n.actual) + sa;
         const T rf1 = v_rcp(f1c);
         const T yf = y * rf1;
         n.add(J, yf * rf1, T(1.0f) - yf);
@@ -1204,11 +1233,10 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
                     e0[j] = init ? e1[j] : t;
                     e1b[j * stride + i] = e1[j];
                 }
-            } else {
-                Mo::expo_old(q1, g1, e0);
             }
             const float y = px.y[i];
             Mo::diff(q0, st, g1, df);
+            if constexpr (!Mo::kStoreE) Mo::expo_old(q1, g1, df, e0);
             const float f0 = Mo::value(q0, e0);
             const float f1 = Mo::value(q1, e1);
             const float dl = Mo::delta(q0, st, df, e0, e1);
@@ -1253,6 +1281,7 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
         n.actual = a1.actual; n.predicted = a1.predicted; n.chi1 = a1.chi1;
     }
     n.reduce(ln);
+    Mo::post_scale(q1, n.A, n.g);  // per-fit column factors the model kept out of its Jacobian rows (no-op for most models)
     if (!MLE && !f_finite(n.chi1)) n.flags |= kFlagNonFinite;
 }
 

@@ -438,7 +438,7 @@ __host__ __device__ inline int group_region(int stride, int ne, int table, int G
 // Gaussian, single exponentials); models with more parameters or more per-pixel state declare kMinCtas = 2 (<= 255
 // registers): measured +28 % (mle) / +37 % (ls) for the 7-parameter elliptical Gaussian
 template <class Mo>
-constexpr int min_ctas() { return Mo::kMinCtas < DPH_MINB ? Mo::kMinCtas : DPH_MINB; }
+constexpr int min_ctas() { return (Mo::kMinCtas < DPH_MINB ? Mo::kMinCtas : DPH_MINB) * 4 / DPH_WARPS; }  // kMinCtas counts four-warp CTAs
 
 template <class Stage, class Mo, int G, class IO>
 __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kernel(const KArgs a) {
