@@ -108,8 +108,8 @@ DPH_HD float v_erf(float a) { return erff(a); }
 DPH_HD f2 v_erf(f2 a) { return f2(erff(a.x), erff(a.y)); }
 DPH_HD float v_max(float a, float b) { return fmaxf(a, b); }
 DPH_HD f2 v_max(f2 a, float b) { return f2(fmaxf(a.x, b), fmaxf(a.y, b)); }
-DPH_HD float v_min3(float a, float b, float c) { return fminf(a, fminf(b, c)); }
-DPH_HD f2 v_min3(f2 a, f2 b, f2 c) { return f2(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y))); }
+DPH_HD float v_min2(float a, float b) { return fminf(a, b); }
+DPH_HD f2 v_min2(f2 a, f2 b) { return f2(fminf(a.x, b.x), fminf(a.y, b.y)); }
 // |a| <= thr ? x : y
 DPH_HD float v_sel_small(float a, float thr, float x, float y) { return fabsf(a) <= thr ? x : y; }
 DPH_HD f2 v_sel_small(f2 a, float thr, f2 x, f2 y) { return f2(fabsf(a.x) <= thr ? x.x : y.x, fabsf(a.y) <= thr ? x.y : y.y); }
@@ -205,6 +205,14 @@ DPH_HD float v_absmax(float a, float b) { return fmaxf(fabsf(a), fabsf(b)); }
 DPH_HD float v_absmax(f2 a, f2 b) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))); }
 DPH_HD float v_absmax(float a) { return fabsf(a); }
 DPH_HD float v_absmax(f2 a) { return fmaxf(fabsf(a.x), fabsf(a.y)); }
+
+// e(new) - e(old) of an exponential whose argument changed by darg: e(old) expm1(darg), or the direct difference of the two
+// values for a large change.  Both are computed and one is selected: putting the rare one behind a warp-uniform branch was
+// measured slower (pre-fit kernel 0.304 -> 0.323 ms per 1e5 fits)
+template <class T>
+DPH_HD T exp_step(T darg, T ea, T eb) {
+    return v_sel_small(darg, kSmallArg, ea * expm1_small(darg), eb - ea);
+}
 
 // ------------------------------------------------------------------------------- small dense algebra
 // packed upper triangle, row-major: (i,j), i <= j
@@ -361,7 +369,7 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     }
     template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
         T darg = f_fma(df.dr2, T(s.nh1), df.r20 * T(s.nds));
-        T de = v_sel_small(darg, kSmallArg, ea[0] * expm1_small(darg), eb[0] - ea[0]);
+        T de = exp_step(darg, ea[0], eb[0]);
         return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d4)));
     }
     template <class T> DPH_HD static T jdx(const Par&, const Step& s, const Diff<T>& df, const T* ea) {
@@ -431,7 +439,7 @@ struct Gauss2DFixed {
     }
     template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
         T darg = df.dr2 * T(s.nh1);
-        T de = v_sel_small(darg, kSmallArg, ea[0] * expm1_small(darg), eb[0] - ea[0]);
+        T de = exp_step(darg, ea[0], eb[0]);
         return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d3)));
     }
     template <class T> DPH_HD static T jdx(const Par&, const Step& s, const Diff<T>& df, const T* ea) {
@@ -521,7 +529,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         T dv2 = dv * f_fma(T(2.0f), ga.v, dv);
         T t = f_fma(du2, T(s.axb), ga.u * ga.u * T(s.dax)) + f_fma(dv2, T(s.ayb), ga.v * ga.v * T(s.day));
         T darg = t * T(-0.5f);
-        T de = v_sel_small(darg, kSmallArg, ea[0] * expm1_small(darg), eb[0] - ea[0]);
+        T de = exp_step(darg, ea[0], eb[0]);
         return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d6)));
     }
     template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& ga, const T* ea) {
@@ -736,7 +744,7 @@ struct MultiExp {
 #pragma unroll
         for (int i = 0; i < NEXP; ++i) {
             T darg = ga.x * T(-s.dk[i]);
-            T de = v_sel_small(darg, kSmallArg, ea[i] * expm1_small(darg), eb[i] - ea[i]);
+            T de = exp_step(darg, ea[i], eb[i]);
             r = f_fma(T(s.da[i]), eb[i], f_fma(T(a.a[i]), de, r));
         }
         return r;
@@ -1110,26 +1118,28 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
         const T rn0 = yf0 - T(1.0f);  // -(1 - y/f0): minus the residual the gradient at the accepted point was summed from 
         // t(f0) - t(f1) = rn0 dl - (y/f0) dl u S(u)   (see neg_series_ln above).  The first-order term goes into the sum on its own,
         // with the very rn0 (an exact product inside the multiply-add): folding it into one factor q = rn0 - (y/f0) u S(u) rounds
-        // q and costs 0.3 % of nfev equality on the golden sets; the second-order term follows as (y/f0 u dl) (-S(u)).
+        // q and costs 0.3 % of nfev equality on the golden sets; the second-order term follows as (y u dl) (-S(u)).
         const T u = dl * rf0;
-        const T yu = yf0 * u;
-        T sa = (yu * dl) * neg_series_ln(u);  // -y (u - ln(1 + u))
+        const T ma = (yf0 * u) * dl;                       // y u^2:  -y (u - ln(1 + u)) = ma (-S(u))
+        n.actual = f_fma(rn0, dl, n.actual) + ma * neg_series_ln(u);
         if (PRED) {
             const T jd = Mo::jdx(q0, st, df, e0);
             const T dp = dl + jd;
             const T up = dp * rf0;
-            T sp = ((yf0 * up) * dp) * neg_series_ln_pred(up);
-            if (v_absmax(u, up) > kSeriesMax) {  // a step that changes this pixel by more than 12 %: rare
-                sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(kLn2), T(0.0f) - u));
-                sp = v_sel_small(up, kSeriesMax, sp, y * f_fma(v_lg2(up + T(1.0f)), T(kLn2), T(0.0f) - up));
+            const T mp = (yf0 * up) * dp;
+            n.predicted = f_fma(rn0, dp, n.predicted) + mp * neg_series_ln_pred(up);
+            if (v_absmax(u, up) > kSeriesMax) {  // a step that changes this pixel by more than 12 %: rare -- the logarithm replaces the series
+                const T la = y * f_fma(v_lg2(u + T(1.0f)), T(kLn2), T(0.0f) - u) - ma * neg_series_ln(u);
+                const T lp = y * f_fma(v_lg2(up + T(1.0f)), T(kLn2), T(0.0f) - up) - mp * neg_series_ln_pred(up);
+                n.actual = n.actual + v_sel_small(u, kSeriesMax, T(0.0f), la);
+                n.predicted = n.predicted + v_sel_small(up, kSeriesMax, T(0.0f), lp);
+                n.lo = v_min2(n.lo, f1c + jd);  // the predicted value f0 (1 + up) can only reach 0 on such a step
             }
-            n.lo = v_min3(n.lo, f1c, f1c + jd);
-            n.predicted = f_fma(rn0, dp, n.predicted) + sp;
-        } else {
-            if (v_absmax(u) > kSeriesMax) sa = v_sel_small(u, kSeriesMax, sa, y * f_fma(v_lg2(u + T(1.0f)), T(kLn2), T(0.0f) - u));
-            n.lo = v_min3(n.lo, f1c, f1c);
+        } else if (v_absmax(u) > kSeriesMax) {
+            const T la = y * f_fma(v_lg2(u + T(1.0f)), T(kLn2), T(0.0f) - u) - ma * neg_series_ln(u);
+            n.actual = n.actual + v_sel_small(u, kSeriesMax, T(0.0f), la);
         }
-        n.actual = f_fma(rn0, dl, n.actual) + sa;
+        n.lo = v_min2(n.lo, f1c);
         const T rf1 = v_rcp(f1c);
         const T yf = y * rf1;
         n.add(J, yf * rf1, T(1.0f) - yf);

@@ -83,6 +83,8 @@ def test_exact_ties_give_the_reference_flag(golden, name):
     assert rep["converged_equal"] == 1.0 and rep["info_equal"] >= 0.999, rep
     plain = host_emu.fit_batch(models.resolve(g["model"], g["consts"]).model_id, g["method"], g["data"], g["p0"], g["xaxis"],
                                consts=g["consts"])
-    same = out["info"] == plain["info"]
-    np.testing.assert_array_equal(out["popt"][same], plain["popt"][same])  # only the tie-broken fits end differently
+    # only the tie-broken fits end differently (one that is sent on and stops one trip later has the same flag, not the same nfev)
+    same = (out["info"] == plain["info"]) & (out["nfev"] == plain["nfev"])
+    assert same.mean() > 0.97
+    np.testing.assert_array_equal(out["popt"][same], plain["popt"][same])
     assert same.mean() > 0.97
