@@ -43,6 +43,22 @@
 #define DPH_PAIR_UNROLL 2  // unroll factor of the pixel-pair loop: two pairs in flight per lane (fits the register bound since the stash)
 #endif
 
+// per model (measured at 1e5 fits per call, one pair against two): elliptical Gaussian +11 %, IRF-convolved decay +14 %,
+// pixel-integrated Gaussians +2..6 % with ONE pair in flight (their loop bodies are large: with two, instruction fetch
+// -- `no_instruction` -- becomes the leading stall); multi-exponentials equal; sampled Gaussians +3-5 % with two
+#ifndef DPH_UNROLL_ELLIP
+#define DPH_UNROLL_ELLIP 1
+#endif
+#ifndef DPH_UNROLL_GINT
+#define DPH_UNROLL_GINT 1
+#endif
+#ifndef DPH_UNROLL_MEXP
+#define DPH_UNROLL_MEXP DPH_PAIR_UNROLL
+#endif
+#ifndef DPH_UNROLL_IRF
+#define DPH_UNROLL_IRF 1
+#endif
+
 namespace dphlm {
 
 constexpr int kPairUnroll = DPH_PAIR_UNROLL;
@@ -298,7 +314,7 @@ DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
 #define DPH_GAUSS2D_MINCTAS 3
 #endif
 struct Gauss2D {  // amp, x0, y0, sigma, offset
-    static constexpr int P = 5, NE = 1, kMinCtas = DPH_GAUSS2D_MINCTAS;
+    static constexpr int P = 5, NE = 1, kMinCtas = DPH_GAUSS2D_MINCTAS, kUnroll = kPairUnroll;
     struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3, ad1, ad2, anh; };  // a*: step from / exponent scale of the accepted point
     struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
     template <class T> struct Geo { T dx, dy, r2; };
@@ -382,7 +398,7 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
 // fixed-width variant for the pixel-centre model; the erf form is Gauss2DIntegratedFixed).  Same step algebra as Gauss2D
 // with d_sigma = 0.
 struct Gauss2DFixed {
-    static constexpr int P = 4, NE = 1, kMinCtas = 3;
+    static constexpr int P = 4, NE = 1, kMinCtas = 3, kUnroll = kPairUnroll;
     struct Par { float amp, x0, y0, off, sig = 1.0f, s2 = 1.0f, nh = -0.5f * 1.4426950408889634f, as2; };
     struct Step { float d0, d1, d2, d3, nh1, ndd, c2, k0; };
     template <class T> struct Geo { T dx, dy, r2; };
@@ -448,10 +464,17 @@ struct Gauss2DFixed {
 };
 
 struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
-    static constexpr int P = 7, NE = 1, kMinCtas = 2;
-    struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy; };
-    struct Step { float d0, d1, d2, d3, d4, d5, d6, cb, sb, dc, dsn, axb, ayb, dax, day, t1, t2; };
-    template <class T> struct Geo { T dx, dy, u, v; };
+#ifndef DPH_ELLIP_MINCTAS
+#define DPH_ELLIP_MINCTAS 2
+#endif
+    // (one pixel pair in flight per lane: with 35 packed accumulators the two-pair loop body outgrows the instruction cache --
+    // `no_instruction` was the leading stall -- and costs 11 %)
+    static constexpr int P = 7, NE = 1, kMinCtas = DPH_ELLIP_MINCTAS, kUnroll = DPH_UNROLL_ELLIP;
+    // ax = 1/sx^2, ay = 1/sy^2; hax, hay: the same times -log2(e)/2 (exponent of ex2); axc .. ayc: products with cos / sin theta
+    struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy, hax, hay, axc, axs, nays, ayc; };
+    // K1..K5: amp_old times the coefficients of u, v, u^2, v^2, u v in J(x_old) . d (see jdx)
+    struct Step { float d0, d1, d2, d6, dc, dsn, haxb, hayb, hdax, hday, t1, t2, K1, K2, K3, K4, K5; };
+    template <class T> struct Geo { T dx, dy, u, v, u2, v2; };
     template <class T> struct Diff { T dx, dy, u, v; };
     static constexpr int kTable = 0;
     static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
@@ -467,28 +490,39 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
 #endif
         q.isx = f_rcp(q.sx); q.isy = f_rcp(q.sy);
         q.ax = q.isx * q.isx; q.ay = q.isy * q.isy;
+        q.hax = -0.5f * kLog2e * q.ax; q.hay = -0.5f * kLog2e * q.ay;
+        q.axc = q.ax * q.c; q.axs = q.ax * q.s; q.nays = -q.ay * q.s; q.ayc = q.ay * q.c;
     }
     template <class T> DPH_HD static void geometry(const Par& q, T cx, T cy, Geo<T>& g) {
         g.dx = cx - T(q.x0); g.dy = cy - T(q.y0);
         g.u = f_fma(T(q.c), g.dx, g.dy * T(q.s));
         g.v = f_fma(T(q.c), g.dy, g.dx * T(-q.s));
+        g.u2 = g.u * g.u; g.v2 = g.v * g.v;
     }
     template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) {
-        e[0] = v_ex2(f_fma(g.u * g.u, T(q.ax), g.v * g.v * T(q.ay)) * T(-0.5f * kLog2e));
+        e[0] = v_ex2(f_fma(g.u2, T(q.hax), g.v2 * T(q.hay)));
     }
     template <class T> DPH_HD static T value(const Par& q, const T* e) { return f_fma(T(q.amp), e[0], T(q.off)); }
+    // Jacobian row without the per-fit factors of its columns (see Gauss2D::jac): (e, e (u ax c - v ay s), e (u ax s + v ay c),
+    // e u^2, e v^2, e u v, 1); post_scale applies (1, amp, amp, amp ax / sx, amp ay / sy, amp (ay - ax), 1) to the sums
     template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
-        T ae = e[0] * T(q.amp);
-        T uax = g.u * T(q.ax), vay = g.v * T(q.ay);
         J[0] = e[0];
-        J[1] = ae * f_fma(uax, T(q.c), vay * T(-q.s));
-        J[2] = ae * f_fma(uax, T(q.s), vay * T(q.c));
-        J[3] = ae * g.u * uax * T(q.isx);
-        J[4] = ae * g.v * vay * T(q.isy);
-        J[5] = ae * g.u * g.v * T(q.ay - q.ax);
+        J[1] = e[0] * f_fma(g.u, T(q.axc), g.v * T(q.nays));
+        J[2] = e[0] * f_fma(g.u, T(q.axs), g.v * T(q.ayc));
+        J[3] = e[0] * g.u2;
+        J[4] = e[0] * g.v2;
+        J[5] = e[0] * (g.u * g.v);
         J[6] = T(1.0f);
     }
-    DPH_HD static void post_scale(const Par&, float*, float*) {}
+    DPH_HD static void post_scale(const Par& q, float* A, float* g) {
+        const float s[P] = {1.0f, q.amp, q.amp, q.amp * q.ax * q.isx, q.amp * q.ay * q.isy, q.amp * (q.ay - q.ax), 1.0f};
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+#pragma unroll
+            for (int j = i; j < P; ++j) A[i * P - (i * (i - 1)) / 2 + (j - i)] *= s[i] * s[j];
+            g[i] *= s[i];
+        }
+    }
     DPH_HD static void eval64(const double* p, const float*, double cx, double cy, double& f, double* J) {
         const double c = cos(p[5]), s = sin(p[5]), dx = cx - p[1], dy = cy - p[2];
         const double u = c * dx + s * dy, v = -s * dx + c * dy, ax = 1.0 / (p[3] * p[3]), ay = 1.0 / (p[4] * p[4]);
@@ -498,8 +532,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         J[3] = ae * u * u * ax / p[3]; J[4] = ae * v * v * ay / p[4]; J[5] = ae * u * v * (ay - ax); J[6] = 1.0;
     }
     DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
-        s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d3 = d[3]; s.d4 = d[4]; s.d5 = d[5]; s.d6 = d[6];
-        s.cb = b.c; s.sb = b.s;
+        s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d6 = d[6];
         // cos/sin increments through the half-angle identities (no cancellation)
         float hs, hc;
         float thm = a.th + 0.5f * d[5];
@@ -511,11 +544,18 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         float sh = sinf(0.5f * d[5]);
         s.dc = -2.0f * hs * sh;
         s.dsn = 2.0f * hc * sh;
-        s.axb = b.ax; s.ayb = b.ay;
-        s.dax = -d[3] * (2.0f * a.sx + d[3]) * a.ax * b.ax;
-        s.day = -d[4] * (2.0f * a.sy + d[4]) * a.ay * b.ay;
-        s.t1 = -f_fma(s.cb, s.d1, s.sb * s.d2);   // rotation of the centre shift, new frame
-        s.t2 = -f_fma(s.cb, s.d2, -s.sb * s.d1);
+        // exponent change = -1/2 (d(u^2) ax_new + u_old^2 d(ax) + the same in v); the factor -1/2 is folded in here
+        s.haxb = -0.5f * b.ax; s.hayb = -0.5f * b.ay;
+        s.hdax = 0.5f * d[3] * (2.0f * a.sx + d[3]) * a.ax * b.ax;
+        s.hday = 0.5f * d[4] * (2.0f * a.sy + d[4]) * a.ay * b.ay;
+        s.t1 = -f_fma(b.c, d[1], b.s * d[2]);   // rotation of the centre shift, new frame
+        s.t2 = -f_fma(b.c, d[2], -b.s * d[1]);
+        // J(x_old) . d = e_old (d0 + amp (u K1' + v K2' + u^2 K3' + v^2 K4' + u v K5')) + d6 with the old point's u, v
+        s.K1 = a.amp * f_fma(a.axc, d[1], a.axs * d[2]);
+        s.K2 = a.amp * f_fma(a.nays, d[1], a.ayc * d[2]);
+        s.K3 = a.amp * a.ax * a.isx * d[3];
+        s.K4 = a.amp * a.ay * a.isy * d[4];
+        s.K5 = a.amp * (a.ay - a.ax) * d[5];
     }
     template <class T> DPH_HD static void diff(const Par& a, const Step& s, const Geo<T>& g1, Diff<T>& df) {
         df.dx = g1.dx + T(s.d1); df.dy = g1.dy + T(s.d2);  // offsets from the OLD centre
@@ -527,21 +567,15 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
         T dv = f_fma(T(s.dc), ga.dy, f_fma(T(-s.dsn), ga.dx, T(s.t2)));
         T du2 = du * f_fma(T(2.0f), ga.u, du);
         T dv2 = dv * f_fma(T(2.0f), ga.v, dv);
-        T t = f_fma(du2, T(s.axb), ga.u * ga.u * T(s.dax)) + f_fma(dv2, T(s.ayb), ga.v * ga.v * T(s.day));
-        T darg = t * T(-0.5f);
+        T darg = f_fma(du2, T(s.haxb), (ga.u * ga.u) * T(s.hdax)) + f_fma(dv2, T(s.hayb), (ga.v * ga.v) * T(s.hday));
         T de = exp_step(darg, ea[0], eb[0]);
         return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d6)));
     }
-    template <class T> DPH_HD static T jdx(const Par& a, const Step& s, const Diff<T>& ga, const T* ea) {
-        T ae = ea[0] * T(a.amp);
-        T uax = ga.u * T(a.ax), vay = ga.v * T(a.ay);
-        T r = f_fma(ea[0], T(s.d0), T(s.d6));
-        r = f_fma(ae * f_fma(uax, T(a.c), vay * T(-a.s)), T(s.d1), r);
-        r = f_fma(ae * f_fma(uax, T(a.s), vay * T(a.c)), T(s.d2), r);
-        r = f_fma(ae * ga.u * uax, T(a.isx * s.d3), r);
-        r = f_fma(ae * ga.v * vay, T(a.isy * s.d4), r);
-        r = f_fma(ae * ga.u * ga.v, T((a.ay - a.ax) * s.d5), r);
-        return r;
+    template <class T> DPH_HD static T jdx(const Par&, const Step& s, const Diff<T>& ga, const T* ea) {
+        T t1 = f_fma(ga.v, T(s.K5), f_fma(ga.u, T(s.K3), T(s.K1)));
+        T t2 = f_fma(ga.v, T(s.K4), T(s.K2));
+        T lin = f_fma(ga.u, t1, f_fma(ga.v, t2, T(s.d0)));
+        return f_fma(ea[0], lin, T(s.d6));
     }
 };
 
@@ -559,7 +593,7 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
 // Then  f_b - f_a = d_amp E_bx E_by + amp_a (dEx E_by + E_ax dEy) + d_off  without cancellation.
 template <bool FIXED>
 struct Gauss2DIntegratedT {
-    static constexpr int P = FIXED ? 4 : 5, NE = 1, kMinCtas = 3, kOff = P - 1;
+    static constexpr int P = FIXED ? 4 : 5, NE = 1, kMinCtas = 3, kOff = P - 1, kUnroll = DPH_UNROLL_GINT;
     static constexpr int kAxisMax = 32;                // ROI side limit (validated by the entry points)
     static constexpr int kTable = 10 * 2 * kAxisMax;   // static bound, used by the covariance kernel
     static constexpr bool kStoreE = false;             // the accepted point's pixel value is E_ax E_ay from the tables
@@ -691,7 +725,7 @@ using Gauss2DIntegratedFixed = Gauss2DIntegratedT<true>;   // (photons, x0, y0, 
 // sum of NEXP exponentials (+ offset): a0, k0, a1, k1, ..., [offset]   (fitfuncs.py:20-52)
 template <int NEXP, bool OFFSET>
 struct MultiExp {
-    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = NEXP, kMinCtas = NEXP >= 3 ? 2 : 3;
+    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = NEXP, kMinCtas = NEXP >= 3 ? 2 : 3, kUnroll = DPH_UNROLL_MEXP;
     struct Par { float a[NEXP], k[NEXP], off; };
     struct Step { float da[NEXP], dk[NEXP], doff; };
     template <class T> struct Geo { T x; };
@@ -772,7 +806,7 @@ struct MultiExp {
 constexpr int kIrfTaps = 32;
 template <int NEXP, bool OFFSET>
 struct MultiExpIrf {
-    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = 2 * NEXP, kMinCtas = 3;
+    static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = 2 * NEXP, kMinCtas = 3, kUnroll = DPH_UNROLL_IRF;
     static constexpr int kHalf = 2 * NEXP * kIrfTaps;  // one buffer: S and T per exponential
     static constexpr int kTable = 2 * kHalf;           // accepted point and trial point; accepting a step flips which is which
     static constexpr bool kStoreE = false;             // C and D of the accepted point are rebuilt from its tables
@@ -1180,7 +1214,7 @@ DPH_HD void trial_pass(const Lanes<G>& ln, const PixelState<Mo::NE>& px, const t
         Acc<P, float> a1;
         const int npair = px.M >> 1;
 #if defined(__CUDA_ARCH__)
-#pragma unroll kPairUnroll
+#pragma unroll Mo::kUnroll
 #endif
         for (int q = ln.lane; q < npair; q += G) {
             const int i = 2 * q;
