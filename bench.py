@@ -318,19 +318,27 @@ def main():
             with torch.cuda.stream(st_):
                 d_probe[k * quarter:(k + 1) * quarter].copy_(h_probe[k * quarter:(k + 1) * quarter], non_blocking=True)
 
+    def probe_single():  # the same bytes as one copy on one stream
+        d_probe.copy_(h_probe, non_blocking=True)
+
     for _ in range(2):
         probe_round()
+        probe_single()
     best_gbs = 0.0
-    for _ in range(3):  # best of three blocks of eight rounds
+    for rep in range(6):  # best of six blocks of eight rounds, alternating eight copies in flight and one large copy
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-        for st_ in probe_streams:
-            st_.wait_event(ev0)
-        for _ in range(8):
-            probe_round()
-        for st_ in probe_streams:
-            torch.cuda.current_stream().wait_stream(st_)
+        if rep % 2 == 0:
+            for st_ in probe_streams:
+                st_.wait_event(ev0)
+            for _ in range(8):
+                probe_round()
+            for st_ in probe_streams:
+                torch.cuda.current_stream().wait_stream(st_)
+        else:
+            for _ in range(8):
+                probe_single()
         ev1.record()
         barrier()
         best_gbs = max(best_gbs, 8 * 8 * quarter * 4 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
@@ -349,7 +357,7 @@ def main():
         h_sets.append((hd, hp))
     h_out = dph.BatchResult(dph.pinned_empty((n, 5)), dph.pinned_empty(n, np.int32), dph.pinned_empty(n, np.int32),
                             dph.pinned_empty(n), None, None)
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 100))  # one pinned result set (3.2 MB) per step
     # one result set per step in flight: the calls are enqueued without waiting (dphlm_fit_batch_host_async), so the upload of
     # one step overlaps the kernels and the result copies of the one before; every step's H2D and D2H is inside the timed region
     h_outs = [h_out] + [dph.BatchResult(dph.pinned_empty((n, 5)), dph.pinned_empty(n, np.int32), dph.pinned_empty(n, np.int32),
@@ -440,8 +448,9 @@ def main():
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
                 # dram__bytes_read+write of the lm() main launch from the ncu --set full capture of this workload
-                # (profiles/r1_ncu_full_v4_gauss2d_11x11_G4.txt); algorithmic: 484 B/fit read again + 32 B/fit written
-                "traffic": 51.2e6 * n / 1e5, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; the main launch, events around it)",
+                # (profiles/r2_final_ncu_full_gauss2d_11x11_G2.txt: 50.85 MB read + 0.1 MB written per 1e5 fits; a constant from
+                # that capture); algorithmic: 484 B/fit read again + 20 B/fit of pre-fit parameters + 32 B/fit written
+                "traffic": 50.95e6 * n / 1e5, "kernel": "dphlm_stage_kernel<StageB<Gauss2D,MLE>> (the lm() loop, lm.py:389-481; the main launch, events around it)",
                 "kernel_ms": k_main * 1e3, "stage_ms": (k_main + k_tail) * 1e3, "share_of_step": (k_main + k_tail) / k_s,
                 "timing_note": "kernel times come from calls with DPHLM_FLAG_TIMING: events between the launches, so the lm() kernel does not "
                                "start early in the slots the pre-fit kernel frees, and nothing is pipelined; `achieved` = lm() flops / stage_ms",
@@ -452,6 +461,14 @@ def main():
                 "prefit_kernel": {"kernel": "dphlm_stage_kernel<StageA<Gauss2D>> (MINPACK pre-fit, lm.py:642-648)", "kernel_ms": k_pre * 1e3,
                                   "achieved": float(np.mean(fl_pre)) / k_pre / 1e12, "flops_per_fit": float(np.mean(fl_pre)) / n},
                 "step": {"achieved": step_tf, "frac": step_tf / fp32_peak_tf, "flops_per_fit": float(np.mean(flops)) / n},
+                # the same flops over the time the headline `value` is measured with (pipelined steps, ms_per_step)
+                "step_at_value": {"achieved": float(np.mean(flops)) / (ms_total / args.steps * 1e-3) / 1e12,
+                                  "frac": float(np.mean(flops)) / (ms_total / args.steps * 1e-3) / 1e12 / fp32_peak_tf},
+                # ncu, sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active of the two main kernels at two lanes per fit
+                # (profiles/r2_final_ncu_full_gauss2d_11x11_G2.txt; a constant copied from that capture, not measured in this run):
+                # the FP32 pipe is busy 61 % (lm()) / 64 % (pre-fit) of the kernels' active cycles.  A packed FFMA2 holds the pipe
+                # for two cycles (profiles/r2_pipes_microbench.txt), and executed flops are ~3x the algorithmic count
+                "fma_pipe_cycles_active_ncu": {"lm_kernel": 0.606, "prefit_kernel": 0.641, "source": "profiles/r2_final_ncu_full_gauss2d_11x11_G2.txt"},
                 "hbm": {"achieved": BYTES_PER_FIT * n / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": BYTES_PER_FIT * n / k_s / 1e9 / hbm_peak, "bytes_per_fit": BYTES_PER_FIT,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"},

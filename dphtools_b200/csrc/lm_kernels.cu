@@ -364,15 +364,15 @@ static int host_enqueue(const dphlm_desc* d, int device, bool async) {
     // kernels cannot start before the first chunk has landed and need longer per fit than the copy does, so the chunks
     // grow: n/10, 2n/10, 3n/10, 4n/10 for a batch up to ~6e5 fits, then the cap.  DPHLM_CHUNK = fixed size (tuning).
     // A call that is enqueued without waiting overlaps with its neighbours anyway (the copy of the next call runs under the
-    // kernels of this one), and small chunks cost kernel efficiency: three equal chunks then (measured at 1e5 fits per call
-    // on one box: 9.25e7 fits/s = 46.6 GB/s of host-to-device copies, against 9.0e7 for two halves and 8.7e7 for the growing
-    // schedule; box-to-box variation of the copy rate is larger than these differences).
+    // kernels of this one), and small chunks cost kernel efficiency: two halves then.  Measured at 1e5 fits per call over 60
+    // calls: 1.05e8 / 1.03e8 / 0.995e8 fits/s for one / two / three chunks (53 GB/s of host-to-device copies: the PCIe link),
+    // 0.9e8 for the growing schedule; over 10 calls, where filling and draining the pipeline shows, three chunks lead by 2 %.
     const long long kChunkMin = 8192, kChunkMax = 262144;
     long long step = d->n_fits / 10;
     if (step < kChunkMin) step = kChunkMin;
     if (step > kChunkMax) step = kChunkMax;
     long long fixed = 0;
-    if (async) fixed = std::min<long long>(std::max<long long>((d->n_fits + 2) / 3, kChunkMin), kChunkMax);
+    if (async) fixed = std::min<long long>(std::max<long long>((d->n_fits + 1) / 2, kChunkMin), kChunkMax);
     if (const char* e = getenv("DPHLM_CHUNK")) { long long v = atoll(e); if (v > 0) fixed = v; }
     std::vector<long long> bounds{0};
     for (long long c = fixed ? fixed : step; bounds.back() < d->n_fits;) {
@@ -383,7 +383,7 @@ static int host_enqueue(const dphlm_desc* d, int device, bool async) {
     }
     // the largest chunk either schedule would make of this batch sizes the slot buffers (so that a blocking call followed by an
     // asynchronous one of the same size does not reallocate them)
-    long long chunk = std::min<long long>(std::max<long long>(4 * step, kChunkMin), kChunkMax);
+    long long chunk = std::min<long long>(std::max<long long>(std::max<long long>(4 * step, (d->n_fits + 1) / 2), kChunkMin), kChunkMax);
     for (size_t i = 1; i < bounds.size(); ++i) chunk = std::max(chunk, bounds[i] - bounds[i - 1]);
     const size_t b_data = align_up(chunk * M * 4), b_par = align_up(chunk * P * 4), b_i = align_up(chunk * 4),
                  b_cnt = align_up(chunk * 16), b_x = align_up(M * 4) + 256;  // xaxis + model constants
