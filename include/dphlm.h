@@ -65,7 +65,7 @@ typedef struct dphlm_desc {
     int32_t* nfev;       /* [n_fits] infodict['nfev'] of stage 2                            (lm.py:489) */
     float* chisq;        /* [n_fits] chi-square at popt (0.5 sum r^2, or Poisson deviance / 2)          */
     float* p_ls;         /* optional [n_fits, n_param]: result of the least-squares pre-fit (lm.py:648) */
-    int32_t* counts;     /* optional [n_fits, 4]: pre-fit evaluations, accepted, rejected steps, 0      */
+    int32_t* counts;     /* optional [n_fits, 4]: pre-fit evaluations, accepted, rejected steps, float64 tie-breaks */
     float* x_acc;        /* optional [n_fits, n_param]: last ACCEPTED point of lm(); infodict['fjac'] and pcov of the
                             reference are evaluated there, one step before popt                 (lm.py:468-473, 489) */
     float ftol, xtol, gtol, factor; /* lm()/leastsq keywords, forwarded to both stages (lm.py:643, 668) */
@@ -91,7 +91,7 @@ typedef struct dphlm_desc {
 /* flags: skip the least-squares pre-fit: `p0` is the start of the lm() loop itself.  This is the reference's second public
  * function, lm(func, x0, ..., method=) (dphtools/utils/lm.py:221-236), as opposed to curve_fit (lm.py:510-685). */
 #define DPHLM_FLAG_SKIP_PREFIT 16
-/* flags: re-decide in float64 the lm() trips whose step is within a factor 64 of the xtol threshold (lm.py:365-367, 430-432).
+/* flags: re-decide in float64 the lm() trips whose step is within a factor 16 of the xtol threshold (lm.py:365-367, 430-432).
  * xtol = 1.49e-8 is four times below float32 resolution of x, so the float32 path splits the fits that end that close --
  * 0.1 % (5-parameter Gaussian) to 2 % (4-parameter models) of a batch -- between info 1 and info 2 by noise; both mean
  * "converged" and the parameters agree to 1e-7 either way.  With this flag those fits get the reference's flag (info equality
@@ -127,11 +127,13 @@ int dphlm_fit_batch_host(const dphlm_desc* d, int device);
 int dphlm_fit_batch_host_async(const dphlm_desc* d, int device);
 int dphlm_host_wait(int device);
 
-/* Parameter covariance of every fit from the model Jacobian at `popt` (DEVICE pointers, asynchronous on `stream`;
+/* Parameter covariance of every fit from the model Jacobian at the given points `popt` (DEVICE pointers, asynchronous on `stream`;
  * uses model, n_param, dim0, dim1, n_fits, xaxis of the descriptor).  pcov is [n_fits, n_param, n_param].
  *   DPHLM_COV_JTJ   pinv(J^T J) of the unweighted Jacobian: the `pcov` curve_fit returns (lm.py:672-677)
  *   DPHLM_COV_CRLB  (J^T diag(1/f) J)^-1: the Poisson Cramer-Rao bound of the fitted parameters
- * A rank-deficient matrix gives NaNs (the reference drops its small singular values instead). */
+ * Computed in float64 from the eigen-decomposition of J^T J: eigenvalues below eps max(M, P) l_max are dropped, so a
+ * rank-deficient Jacobian gives the pseudo-inverse like the reference's singular-value cut (lm.py:675).  For the reference's
+ * pcov pass `x_acc` of dphlm_fit_batch (the last ACCEPTED point, where lm() evaluates fjac), not popt. */
 enum dphlm_cov_kind { DPHLM_COV_JTJ = 0, DPHLM_COV_CRLB = 1 };
 int dphlm_covariance(const dphlm_desc* d, const float* popt, float* pcov, int kind, void* stream);
 
