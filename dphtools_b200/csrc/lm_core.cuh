@@ -1109,6 +1109,9 @@ DPH_HD float mle_term_direct(float f, float y) {
 }
 DPH_HD f2 mle_term_direct(f2 f, f2 y) { return f2(mle_term_direct(f.x, y.x), mle_term_direct(f.y, y.y)); }
 DPH_HD float clamp_nonneg(float f) { return f <= 0.0f ? 0.0f : f; }  // lm.py:117
+// y ln(q) for q = y / f > 0, and 0 where y = 0 (the reference's zeroing rule)
+DPH_HD float v_ylog(float y, float q) { return y > 0.0f ? y * kLn2 * f_lg2(q) : 0.0f; }
+DPH_HD f2 v_ylog(f2 y, f2 q) { return f2(v_ylog(y.x, q.x), v_ylog(y.y, q.y)); }
 
 // MLE weights at a model value f (already clamped): w = y/f^2, res = 1 - y/f; invalid -> (0, 1)  (lm.py:86-102)
 DPH_HD void mle_weights(float f, float y, float& w, float& res) {
@@ -1177,7 +1180,9 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
         const T rf1 = v_rcp(f1c);
         const T yf = y * rf1;
         n.add(J, yf * rf1, T(1.0f) - yf);
-        if (want_chi) n.chi1 = n.chi1 + (mle_term_direct(f1c, y) - y);
+        // chi-square itself (first pass of a fit only): f - y - y ln(f / y) = (f - y) + y ln(y / f), with the y / f the weights
+        // are made of -- one logarithm per pixel; y = 0 contributes f (lm.py:70-78)
+        if (want_chi) n.chi1 = n.chi1 + ((f1c - y) + v_ylog(y, yf));
     } else {
         const T r0 = f0 - y, r1 = f1 - y;
         n.actual = n.actual - dl * f_fma(T(0.5f), dl, r0);
