@@ -199,20 +199,14 @@ constexpr float kSmallArg = 0.0625f;
 //   t(f0) - t(f1) = (y/f0 - 1) (f1 - f0) - y u^2 S(u),     S(u) = 1/2 - u/3 + u^2/4 - ...   (u - ln(1 + u) = u^2 S(u))
 // The first-order term uses the very residual 1 - y/f0 the gradient at the accepted point was summed from (same inputs, same
 // instructions), so first-order term and step stay consistent down to rounding: that, not the accuracy of the logarithm,
-// is what keeps the signs of reductions ~1e-9 of chi-square right.  The series is cut at degree 3 (truncation u^4/6 of S: 8e-5 of the
-// second-order term at the switch point |u| = 1/8, on steps whose reduction is far above the tolerances); beyond the switch
-// point -- a step that changes a pixel's model value by more than 12 % -- a rarely taken branch substitutes the logarithm.
+// is what keeps the signs of reductions ~1e-9 of chi-square right.  The series is short (see neg_series_ln); beyond the switch
+// point |u| = 1/8 -- a step that changes a pixel's model value by more than 12 % -- a rarely taken branch substitutes the logarithm.
 constexpr float kSeriesMax = 0.125f;
-// -S(u): the sign is folded into the coefficients
+// -S(u), degree 2: the sign is folded into the coefficients.  Truncation u^3/5 of S: 8e-4 of the second-order term at the switch
+// point, 1e-9 at the |u| ~ 1e-3 of the last trips, where the tolerances are decided (degrees 3 and 4 give the same flags and
+// the same nfev on every golden fit).
 template <class T>
-DPH_HD T neg_series_ln(T u) {  // degree 3 (truncation u^4/6: below 1e-4 of the second-order term at the switch point)
-    T p = T(0.2f);
-    p = f_fma(p, u, T(-0.25f));
-    p = f_fma(p, u, T(1.0f / 3.0f));
-    return f_fma(p, u, T(-0.5f));
-}
-template <class T>
-DPH_HD T neg_series_ln_pred(T u) {  // degree 2 (the predicted reduction is only compared with the actual one at the 1 % level)
+DPH_HD T neg_series_ln(T u) {
     T p = T(-0.25f);
     p = f_fma(p, u, T(1.0f / 3.0f));
     return f_fma(p, u, T(-0.5f));
@@ -315,24 +309,23 @@ DPH_HD float quad_form(const float* A, const float* p) {  // p^T A p
 #endif
 struct Gauss2D {  // amp, x0, y0, sigma, offset
     static constexpr int P = 5, NE = 1, kMinCtas = DPH_GAUSS2D_MINCTAS, kUnroll = kPairUnroll;
-    struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3, ad1, ad2, anh; };  // a*: step from / exponent scale of the accepted point
-    struct Step { float d0, d1, d2, d4, nh1, nds, ndd, c2, c3, k0; };
+    struct Par { float amp, x0, y0, sig, off, s2, s3, nh, as2, as3, anh; };  // anh: exponent scale of the accepted point
+    // ad1, ad2: the REALISED centre step (fill_tables); k1, k2: the exponent change is k1 dot + k2 + nds r2_old
+    struct Step { float d0, d1, d2, d4, nds, c2, c3, k0, k1, k2, ad1, ad2; };
     template <class T> struct Geo { T dx, dy, r2; };
-    template <class T> struct Diff { T dot, dr2, r20; };
+    template <class T> struct Diff { T dot, r20; };
     static constexpr int kTable = 0;
     static constexpr bool kStoreE = DPH_GAUSS2D_STORE;  // false: the accepted point's exponential is recomputed, nothing per pixel is kept
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par& q0, Par& q1, Step&, float*, int, int, int) {
-        q1.ad1 = q1.x0 - q0.x0; q1.ad2 = q1.y0 - q0.y0; q1.anh = q0.nh;
+    template <class L> DPH_HD static void fill_tables(const L&, const Par& q0, Par& q1, Step& st, float*, int, int, int) {
+        st.ad1 = q1.x0 - q0.x0; st.ad2 = q1.y0 - q0.y0; q1.anh = q0.nh;
     }
-    // The accepted point's exponential, from the REALISED step (ad1 = x0_new - x0_old is exact in float32, so dxa is cx - x0_old
-    // to one rounding).  Not from the r2_old that diff() forms out of the nominal step: x0 + d rounds, the two differ by up to
-    // half an ulp of x0, and that much inconsistency between this value and the one the gradient of the accepted point was
-    // summed from is enough to lose the last trips (tried: nfev equality 95 % -> 77 %, 0.2 % of the fits no longer converge).
-    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, const Diff<T>&, T* e) {
-        const T dxa = g.dx + T(q.ad1), dya = g.dy + T(q.ad2);
-        e[0] = v_ex2(f_fma(dxa, dxa, dya * dya) * T(q.anh));
-    }
+    // The accepted point's exponential, from the r2 there that diff() forms out of the REALISED step (ad1 = x0_new - x0_old is
+    // exact in float32, so dx + ad1 is cx - x0_old to one rounding, like in the pass that evaluated that point).  Forming r2_old
+    // from the nominal step instead -- x0 + d rounds, the two differ by up to half an ulp of x0 -- makes this value inconsistent
+    // with the one the gradient of the accepted point was summed from, which is enough to lose the last trips (tried: nfev
+    // equality 95 % -> 77 %, 0.2 % of the fits no longer converge).
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>&, const Diff<T>& df, T* e) { e[0] = v_ex2(df.r20 * T(q.anh)); }
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sig = p[3]; q.off = p[4];
@@ -371,20 +364,22 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
     }
     DPH_HD static void prepare_step(const Par& a, const Par& b, const float* d, Step& s) {
         s.d0 = d[0]; s.d1 = d[1]; s.d2 = d[2]; s.d4 = d[4];
-        s.nh1 = -0.5f * b.s2;                                             // -1/(2 sigma_new^2)
+        const float nh1 = -0.5f * b.s2;                                   // -1/(2 sigma_new^2)
         s.nds = d[3] * (2.0f * a.sig + d[3]) * 0.5f * a.s2 * b.s2;        // -(1/(2 s_n^2) - 1/(2 s_o^2))
-        s.ndd = -f_fma(d[1], d[1], d[2] * d[2]);
+        const float ndd = -f_fma(d[1], d[1], d[2] * d[2]);
         s.c2 = a.amp * a.s2; s.c3 = a.amp * a.s3 * d[3];
-        s.k0 = f_fma(-s.c2, s.ndd, d[0]);                                 // d0 + c2 (d1^2 + d2^2)
+        s.k0 = f_fma(-s.c2, ndd, d[0]);                                   // d0 + c2 (d1^2 + d2^2)
+        // exponent change = nh1 (r2_new - r2_old) + nds r2_old, with r2_new - r2_old = -2 dot - (d1^2 + d2^2)
+        s.k1 = -2.0f * nh1; s.k2 = ndd * nh1;
     }
-    // per-pixel step quantities, from the geometry at the NEW point (dx_old = dx_new + d1, ...)
+    // per-pixel step quantities, from the geometry at the NEW point (dx_old = dx_new + step, ...)
     template <class T> DPH_HD static void diff(const Par&, const Step& s, const Geo<T>& g1, Diff<T>& df) {
         df.dot = f_fma(g1.dx, T(s.d1), g1.dy * T(s.d2));
-        df.dr2 = f_fma(T(-2.0f), df.dot, T(s.ndd));  // r2_new - r2_old
-        df.r20 = g1.r2 - df.dr2;                     // r2_old
+        const T dxa = g1.dx + T(s.ad1), dya = g1.dy + T(s.ad2);
+        df.r20 = f_fma(dxa, dxa, dya * dya);         // r2_old
     }
     template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
-        T darg = f_fma(df.dr2, T(s.nh1), df.r20 * T(s.nds));
+        T darg = f_fma(df.dot, T(s.k1), f_fma(df.r20, T(s.nds), T(s.k2)));
         T de = exp_step(darg, ea[0], eb[0]);
         return f_fma(T(s.d0), eb[0], f_fma(T(a.amp), de, T(s.d4)));
     }
@@ -1164,10 +1159,10 @@ DPH_HD void pixel_regular(const typename Mo::Par& q0, const typename Mo::Par& q1
             const T dp = dl + jd;
             const T up = dp * rf0;
             const T mp = (yf0 * up) * dp;
-            n.predicted = f_fma(rn0, dp, n.predicted) + mp * neg_series_ln_pred(up);
+            n.predicted = f_fma(rn0, dp, n.predicted) + mp * neg_series_ln(up);
             if (v_absmax(u, up) > kSeriesMax) {  // a step that changes this pixel by more than 12 %: rare -- the logarithm replaces the series
                 const T la = y * f_fma(v_lg2(u + T(1.0f)), T(kLn2), T(0.0f) - u) - ma * neg_series_ln(u);
-                const T lp = y * f_fma(v_lg2(up + T(1.0f)), T(kLn2), T(0.0f) - up) - mp * neg_series_ln_pred(up);
+                const T lp = y * f_fma(v_lg2(up + T(1.0f)), T(kLn2), T(0.0f) - up) - mp * neg_series_ln(up);
                 n.actual = n.actual + v_sel_small(u, kSeriesMax, T(0.0f), la);
                 n.predicted = n.predicted + v_sel_small(up, kSeriesMax, T(0.0f), lp);
                 n.lo = v_min2(n.lo, f1c + jd);  // the predicted value f0 (1 + up) can only reach 0 on such a step
