@@ -466,9 +466,9 @@ def main():
                                   "frac": float(np.mean(flops)) / (ms_total / args.steps * 1e-3) / 1e12 / fp32_peak_tf},
                 # ncu, sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active of the two main kernels at two lanes per fit
                 # (profiles/r2_final_ncu_full_gauss2d_11x11_G2.txt; a constant copied from that capture, not measured in this run):
-                # the FP32 pipe is busy 61 % (lm()) / 64 % (pre-fit) of the kernels' active cycles.  A packed FFMA2 holds the pipe
+                # the FP32 pipe is busy 60 % (lm()) / 62 % (pre-fit) of the kernels' active cycles.  A packed FFMA2 holds the pipe
                 # for two cycles (profiles/r2_pipes_microbench.txt), and executed flops are ~3x the algorithmic count
-                "fma_pipe_cycles_active_ncu": {"lm_kernel": 0.606, "prefit_kernel": 0.641, "source": "profiles/r2_final_ncu_full_gauss2d_11x11_G2.txt"},
+                "fma_pipe_cycles_active_ncu": {"lm_kernel": 0.603, "prefit_kernel": 0.618, "source": "profiles/r2_final_ncu_full_gauss2d_11x11_G2.txt"},
                 "hbm": {"achieved": BYTES_PER_FIT * n / k_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": BYTES_PER_FIT * n / k_s / 1e9 / hbm_peak, "bytes_per_fit": BYTES_PER_FIT,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"},
