@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--fits", type=int, default=N_FITS, help="fits per GPU and step")
     ap.add_argument("--group-lanes", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs2", action="store_true", help="skip the informational 1e7 7x7 block (BASELINE configs[2])")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample SM clocks through NVML (diagnostic)")
     ap.add_argument("--workload", default="c2", help="c2 = the headline configuration (default); c3, c4, c4ls, c5, c6, c9: the other "
                     "BASELINE / SURVEY configurations, one GPU, one informational line each (scripts/bench_configs.py)")
@@ -407,6 +408,29 @@ def main():
         dist.all_reduce(t_u16, op=dist.ReduceOp.MAX)
     e2e_u16 = world * n * e2e_steps / float(t_u16.item())
 
+    # ---- informational: BASELINE configs[2] -- 1e7 symmetric-Gaussian MLE fits on 7x7 ROIs, sharded over the ranks (strong
+    # scaling: every rank fits 1e7 / world of them in ONE call; generated on the device)
+    c2_block = None
+    if not args.no_configs2:
+        n_c2 = 10_000_000 // world
+        c2_data, c2_p0 = synth.gauss2d_rois_device(n_c2, 7, 77 + rank, dev, jitter=0.75)
+        dph.curve_fit_batch(models.gauss2d, c2_data[:200000], c2_p0[:200000], "mle")  # warm the 7x7 kernels
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        r_c2 = dph.curve_fit_batch(models.gauss2d, c2_data, c2_p0, "mle")
+        ev1.record()
+        barrier()
+        ms_c2 = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+        conv_c2 = ((r_c2.info >= 1) & (r_c2.info <= 4)).double().mean().reshape(1)
+        if world > 1:
+            dist.all_reduce(ms_c2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(conv_c2, op=dist.ReduceOp.SUM)
+        c2_block = {"workload": "1e7 symmetric 2D Gaussian MLE fits, 7x7 ROIs, sharded across the ranks (BASELINE configs[2]); one call per rank, "
+                                "inputs resident, generated on the device", "fits": n_c2 * world, "scaling": "strong", "ms": float(ms_c2.item()),
+                    "value": n_c2 * world / (float(ms_c2.item()) * 1e-3), "unit": "fits/s", "converged_fraction": float(conv_c2.item()) / world}
+        del c2_data, c2_p0, r_c2
+
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join(timeout=2)
@@ -474,6 +498,7 @@ def main():
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback"},
             },
             "clocks": sampler.summary(),
+            "configs2": c2_block,
         }
         if not args.no_cpu and world == 1:
             cores = os.cpu_count()

@@ -57,6 +57,39 @@ def gauss2d_rois(n, size=11, seed=0, photons=(100.0, 5000.0), sigma=(1.0, 1.6), 
     return dict(data=data, p0=gauss2d_p0(data), truth=truth, xaxis=None)
 
 
+def gauss2d_rois_device(n, size, seed, device, photons=(100.0, 5000.0), sigma=(1.0, 1.6), jitter=1.0, bg=(1.0, 10.0), chunk=1 << 20):
+    """:func:`gauss2d_rois` generated on a CUDA device with torch (``torch.Generator(device).manual_seed`` +
+    ``torch.poisson`` for the large on-device batches, e.g. the 1e7 7x7 ROIs of BASELINE configs[2]).  Returns device tensors
+    ``(data [n, size, size] float32, p0 [n, 5] float32)``; same distributions and the same p0 recipe as the host generator."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    c = (size - 1) / 2
+    data = torch.empty((n, size, size), dtype=torch.float32, device=device)
+    p0 = torch.empty((n, 5), dtype=torch.float32, device=device)
+    yy, xx = torch.meshgrid(torch.arange(size, device=device, dtype=torch.float32), torch.arange(size, device=device, dtype=torch.float32), indexing="ij")
+    xx, yy = xx.reshape(1, -1), yy.reshape(1, -1)
+
+    def uni(lo, hi, m):
+        return lo + (hi - lo) * torch.rand((m, 1), device=device, generator=g, dtype=torch.float32)
+
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        nph, sig = uni(*photons, m), uni(*sigma, m)
+        x0, y0, off = c + uni(-jitter, jitter, m), c + uni(-jitter, jitter, m), uni(*bg, m)
+        mu = nph / (2 * np.pi * sig**2) * torch.exp(-((xx - x0) ** 2 + (yy - y0) ** 2) / (2 * sig**2)) + off
+        d = torch.poisson(mu, generator=g)
+        data[lo : lo + m] = d.reshape(m, size, size)
+        mx, mn = d.max(1).values, d.min(1).values
+        p0[lo : lo + m, 0] = mx - mn
+        p0[lo : lo + m, 1] = c
+        p0[lo : lo + m, 2] = c
+        p0[lo : lo + m, 3] = 1.3
+        p0[lo : lo + m, 4] = torch.clamp(mn, min=0.5)
+    return data, p0
+
+
 def gauss2d_integrated_rois(n, size=11, seed=0, photons=(100.0, 5000.0), sigma=(1.0, 1.6), jitter=1.0, bg=(1.0, 10.0)):
     """Pixel-integrated Gaussian spots; ``p0 = (sum(data - min), centre, centre, 1.3, max(min, 0.5))``."""
     rng = np.random.default_rng(seed)
