@@ -1,4 +1,4 @@
-# usage: _run_env.sh VAR v1 v2 ... ; quick_rate.py under each value of an environment variable (development aid)
+# usage: ab_envvar.sh VAR v1 v2 ... ; quick_rate.py under each value of an environment variable (development aid)
 cd /root/repo
 var=$1; shift
 for rep in 1 2; do

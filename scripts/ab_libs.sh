@@ -1,4 +1,4 @@
-# usage: _run_ab.sh libA libB ... ; alternates quick_rate.py over the given libraries (development aid)
+# usage: ab_libs.sh libA libB ... ; alternates quick_rate.py over the given libraries (development aid)
 cd /root/repo
 for rep in 1 2 3; do
 for lib in "$@"; do
