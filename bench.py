@@ -468,7 +468,7 @@ def main():
                                   "note": "bare pinned host-to-device copy of one step's inputs, all ranks at once (slowest rank): what the platform allows end to end"},
                     "uint16_input": {"value": e2e_u16, "h2d_bytes_per_step": n * (ROI * ROI * 2 + 5 * 4),
                                      "note": "informational: same call with uint16 camera counts as host input"}},
-            "gpu_launches": 4 * args.steps,  # pre-fit + lm() main launches and their two straggler follow-ups
+            "gpu_launches": 5 * args.steps,  # per step: the preparation launch, pre-fit + lm() main launches and their two straggler pollers
             "roofline": {
                 "bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
                 # dram__bytes_read+write of the lm() main launch from the ncu --set full capture of this workload
