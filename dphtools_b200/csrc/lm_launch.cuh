@@ -78,6 +78,7 @@ struct KArgs {
     int max_backlog;        // parked fits waiting for a poller beyond which the main kernels stop parking
     int on_demand_tail;     // != 0: the last wave of fits is claimed on demand, not ahead (IoDevice::stage)
     int skip_prefit;        // host-side only: DPHLM_FLAG_SKIP_PREFIT
+    int no_vec16;           // tuning aid (DPHLM_NO_VEC16): stage with 4-byte copies even where 16-byte ones are possible
     long long n_fits;
     int h, w;
     Options opt;
@@ -104,6 +105,10 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {  // both 16-byte aligned
+    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // release / acquire on a word another kernel of the same call polls
@@ -115,12 +120,14 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 
 constexpr int kStageExtra = 8;  // floats after the staged ROI: start parameters (<= 7) and one int
+__device__ __forceinline__ bool getenv_no_vec16(const KArgs& a) { return a.no_vec16 != 0; }
 
 template <class Stage, class Mo, int G, bool MAIN, bool MLE, bool RESUME>
 struct IoDevice {
     const KArgs& a;
     float* ynext;          // staging buffer [stride + kStageExtra] of this group
     long long next = -1;   // index of the staged fit, -1: nothing staged yet
+    bool vec16 = false;    // 128-bit staging copies: ROI size a multiple of 16 bytes and both staging buffers 16-byte aligned
 
     __device__ int budget() const { return (RESUME || a.budget <= 0 || a.produce.cap <= 0) ? 0x7fffffff : a.budget; }
     __device__ const float* consts() const { return a.consts; }
@@ -194,7 +201,11 @@ struct IoDevice {
         next = (long long)idx;
         if (next >= a.n_fits) return;
         const float* d = a.data + idx * M;
-        for (int i = ln.lane; i < M; i += G) cp_async4(ynext + i, d + i);
+        if (vec16) {
+            for (int i = 4 * ln.lane; i < M; i += 4 * G) cp_async16(ynext + i, d + i);
+        } else {
+            for (int i = ln.lane; i < M; i += G) cp_async4(ynext + i, d + i);
+        }
         const float* ps = (MAIN ? a.p_ls : a.p0) + idx * P;
         for (int k = ln.lane; k < P; k += G) cp_async4(ynext + stride + k, ps + k);
         if (MAIN && ln.lane == 0) cp_async4(ynext + stride + 7, a.ier + idx);
@@ -462,6 +473,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
     px.stash = base + region - stash_floats(G, Mo::kStoreE);
     px.w = a.w;
     IO io{a, base + stride + kStageExtra};
+    // ROIs whose size is a multiple of 16 bytes (8x8, 12x12, 256-bin histograms ...) are staged with 128-bit copies; an 11x11
+    // ROI (484 B) is only 4-byte aligned in the batch ("Staging")
+    io.vec16 = !getenv_no_vec16(a) && (M % 4 == 0) && ((reinterpret_cast<size_t>(a.data) & 15) == 0) &&
+               (((__cvta_generic_to_shared(base) | __cvta_generic_to_shared(base + stride + kStageExtra)) & 15) == 0);
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
     if (a.exit_counter) {  // tell the pollers fed by this kernel when its last CTA has gone
         __syncthreads();
@@ -742,6 +757,7 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     KArgs a = a0;
     a.counter = counters;
     a.on_demand_tail = getenv("DPHLM_NO_ON_DEMAND_TAIL") ? 0 : 1;  // tuning aid
+    a.no_vec16 = getenv("DPHLM_NO_VEC16") ? 1 : 0;                  // tuning aid
     a.produce = a.consume[0] = a.consume[1] = none;
     a.wait_done[0] = a.wait_done[1] = nullptr;
     a.exit_counter = a.done_flag = nullptr;

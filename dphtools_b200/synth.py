@@ -238,6 +238,7 @@ def multi_exp_irf_hists(n, bins=256, seed=0, dt=0.05, m0=8):
 WORKLOADS = {
     "c1_gauss2d_15": lambda n, seed=0: gauss2d_rois(n, 15, seed, photons=(1500.0, 1500.0), sigma=(1.38, 1.38)),
     "c2_gauss2d_11": lambda n, seed=0: gauss2d_rois(n, 11, seed),
+    "c2_gauss2d_12": lambda n, seed=0: gauss2d_rois(n, 12, seed),  # 576-byte ROIs: 16-byte aligned in the batch (128-bit staging)
     "c3_gauss2d_7": lambda n, seed=0: gauss2d_rois(n, 7, seed, jitter=0.75),
     "c4_ellip_15": lambda n, seed=0: gauss2d_elliptical_rois(n, 15, seed),
     "c5_multiexp_256": lambda n, seed=0: multi_exp_hists(n, 256, seed),
