@@ -218,3 +218,33 @@ def test_exact_ties_give_the_reference_flag_on_gpu(golden, name):
     assert rep["converged_equal"] == 1.0 and rep["info_equal"] >= 0.999 and rep["within_rtol"] >= 0.9998, rep
     h = dph.curve_fit_batch(model, g["data"][:512], g["p0"][:512], g["method"], g["xaxis"], exact_ties=True)
     np.testing.assert_array_equal(h.info, out["info"][:512])
+
+
+def test_128_bit_staging_changes_nothing(monkeypatch):
+    """ROIs of a multiple of 16 bytes (12x12; 256-bin histograms) are staged with 16-byte cp.async (lm_launch.cuh: vec16); the
+    4-byte path (DPHLM_NO_VEC16) must give the same bits.  A batch pointer that is not 16-byte aligned falls back by itself."""
+    from dphtools_b200 import synth
+
+    for wl, model, lanes in (("c2_gauss2d_12", models.gauss2d, 4), ("c5_multiexp_256", models.multi_exp, 16)):
+        w = synth.WORKLOADS[wl](3000, seed=5)
+        data, p0 = torch.from_numpy(w["data"]).cuda(), torch.from_numpy(w["p0"]).cuda()
+        outs = []
+        for off in (False, True):
+            if off:
+                monkeypatch.setenv("DPHLM_NO_VEC16", "1")
+            else:
+                monkeypatch.delenv("DPHLM_NO_VEC16", raising=False)
+            r = dph.curve_fit_batch(model, data, p0, "mle", w["xaxis"], group_lanes=lanes)
+            torch.cuda.synchronize()
+            outs.append((r.popt.cpu().numpy(), r.info.cpu().numpy(), r.nfev.cpu().numpy()))
+        monkeypatch.delenv("DPHLM_NO_VEC16", raising=False)
+        for a, b in zip(outs[0], outs[1]):
+            np.testing.assert_array_equal(a, b)
+        assert ((outs[0][1] >= 1) & (outs[0][1] <= 4)).mean() > 0.99
+        # a view that starts one ROI into an allocation of 4-byte alignment only: offset by one float
+        flat = torch.empty(data.numel() + 1, device="cuda", dtype=torch.float32)
+        shifted = flat[1:].view_as(data)
+        shifted.copy_(data)
+        r = dph.curve_fit_batch(model, shifted, p0, "mle", w["xaxis"], group_lanes=lanes)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(r.popt.cpu().numpy(), outs[0][0])
