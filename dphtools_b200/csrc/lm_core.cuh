@@ -718,27 +718,40 @@ using Gauss2DIntegrated = Gauss2DIntegratedT<false>;       // (photons, x0, y0, 
 using Gauss2DIntegratedFixed = Gauss2DIntegratedT<true>;   // (photons, x0, y0, offset), sigma = consts[0]
 
 // sum of NEXP exponentials (+ offset): a0, k0, a1, k1, ..., [offset]   (fitfuncs.py:20-52)
+#ifndef DPH_MEXP_STORE
+#define DPH_MEXP_STORE false
+#endif
 template <int NEXP, bool OFFSET>
 struct MultiExp {
     static constexpr int P = 2 * NEXP + (OFFSET ? 1 : 0), NE = NEXP, kMinCtas = NEXP >= 3 ? 2 : 3, kUnroll = DPH_UNROLL_MEXP;
-    struct Par { float a[NEXP], k[NEXP], off; };
+    struct Par { float a[NEXP], k[NEXP], off, kl[NEXP], kla[NEXP]; };  // kl = -log2(e) k; kla: the same of the accepted point
     struct Step { float da[NEXP], dk[NEXP], doff; };
     template <class T> struct Geo { T x; };
     template <class T> struct Diff { T x; };
     static constexpr int kTable = 0;
-    static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
+    // false: the accepted point's exponentials are recomputed from its rates (the same instruction on the same inputs as in the
+    // pass that evaluated that point, so bit for bit the values the gradient was summed from) instead of kept per bin in shared
+    // memory: two more MUFU per bin and exponential against a 64-bit load and store
+    static constexpr bool kStoreE = DPH_MEXP_STORE;
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
+    template <class L> DPH_HD static void fill_tables(const L&, const Par& q0, Par& q1, Step&, float*, int, int, int) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) q1.kla[i] = q0.kl[i];
+    }
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
 #pragma unroll
-        for (int i = 0; i < NEXP; ++i) { q.a[i] = p[2 * i]; q.k[i] = p[2 * i + 1]; }
+        for (int i = 0; i < NEXP; ++i) { q.a[i] = p[2 * i]; q.k[i] = p[2 * i + 1]; q.kl[i] = -kLog2e * q.k[i]; }
         q.off = OFFSET ? p[2 * NEXP] : 0.0f;
     }
     template <class T> DPH_HD static void geometry(const Par&, T cx, T, Geo<T>& g) { g.x = cx; }
     template <class T> DPH_HD static void expo(const Par& q, const Geo<T>& g, T* e) {
 #pragma unroll
-        for (int i = 0; i < NEXP; ++i) e[i] = v_ex2(g.x * T(-kLog2e * q.k[i]));
+        for (int i = 0; i < NEXP; ++i) e[i] = v_ex2(g.x * T(q.kl[i]));
+    }
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, const Diff<T>&, T* e) {
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) e[i] = v_ex2(g.x * T(q.kla[i]));
     }
     template <class T> DPH_HD static T value(const Par& q, const T* e) {
         T f = T(q.off);
@@ -746,12 +759,24 @@ struct MultiExp {
         for (int i = 0; i < NEXP; ++i) f = f_fma(T(q.a[i]), e[i], f);
         return f;
     }
-    template <class T> DPH_HD static void jac(const Par& q, const Geo<T>& g, const T* e, T* J) {
+    // Jacobian row without the per-fit factor -a_i of the rate columns (see Gauss2D::jac): (e_i, x e_i, ..., 1)
+    template <class T> DPH_HD static void jac(const Par&, const Geo<T>& g, const T* e, T* J) {
 #pragma unroll
-        for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[i]; J[2 * i + 1] = g.x * e[i] * T(-q.a[i]); }
+        for (int i = 0; i < NEXP; ++i) { J[2 * i] = e[i]; J[2 * i + 1] = g.x * e[i]; }
         if (OFFSET) J[2 * NEXP] = T(1.0f);
     }
-    DPH_HD static void post_scale(const Par&, float*, float*) {}
+    DPH_HD static void post_scale(const Par& q, float* A, float* g) {
+        float s[P];
+#pragma unroll
+        for (int i = 0; i < NEXP; ++i) { s[2 * i] = 1.0f; s[2 * i + 1] = -q.a[i]; }
+        if (OFFSET) s[2 * NEXP] = 1.0f;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+#pragma unroll
+            for (int j = i; j < P; ++j) A[i * P - (i * (i - 1)) / 2 + (j - i)] *= s[i] * s[j];
+            g[i] *= s[i];
+        }
+    }
     DPH_HD static void eval64(const double* p, const float*, double cx, double, double& f, double* J) {
         f = OFFSET ? p[2 * NEXP] : 0.0;
 #pragma unroll
