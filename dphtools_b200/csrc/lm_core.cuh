@@ -466,15 +466,31 @@ struct Gauss2DElliptical {  // amp, x0, y0, sigma_x, sigma_y, theta, offset
     // `no_instruction` was the leading stall -- and costs 11 %)
     static constexpr int P = 7, NE = 1, kMinCtas = DPH_ELLIP_MINCTAS, kUnroll = DPH_UNROLL_ELLIP;
     // ax = 1/sx^2, ay = 1/sy^2; hax, hay: the same times -log2(e)/2 (exponent of ex2); axc .. ayc: products with cos / sin theta
-    struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy, hax, hay, axc, axs, nays, ayc; };
+    // o_*, ad1, ad2 (fill_tables): cos, sin and exponent scales of the accepted point and the REALISED centre step to it
+    struct Par { float amp, x0, y0, sx, sy, th, off, c, s, ax, ay, isx, isy, hax, hay, axc, axs, nays, ayc, o_c, o_s, o_hax, o_hay, ad1, ad2; };
     // K1..K5: amp_old times the coefficients of u, v, u^2, v^2, u v in J(x_old) . d (see jdx)
     struct Step { float d0, d1, d2, d6, dc, dsn, haxb, hayb, hdax, hday, t1, t2, K1, K2, K3, K4, K5; };
     template <class T> struct Geo { T dx, dy, u, v, u2, v2; };
     template <class T> struct Diff { T dx, dy, u, v; };
     static constexpr int kTable = 0;
-    static constexpr bool kStoreE = true;  // the per-pixel values of the accepted point are kept in shared memory
+#ifndef DPH_ELLIP_STORE
+#define DPH_ELLIP_STORE false
+#endif
+    // false: the accepted point's exponential is recomputed -- its rotated offsets from the REALISED centre step with the very
+    // instruction sequence of geometry(), so bit for bit the value of the pass that evaluated that point (see Gauss2D::expo_old)
+    // -- instead of kept per pixel in shared memory; that halves the shared memory of a fit and makes four-lane groups possible
+    static constexpr bool kStoreE = DPH_ELLIP_STORE;
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
+    template <class L> DPH_HD static void fill_tables(const L&, const Par& q0, Par& q1, Step&, float*, int, int, int) {
+        q1.o_c = q0.c; q1.o_s = q0.s; q1.o_hax = q0.hax; q1.o_hay = q0.hay;
+        q1.ad1 = q1.x0 - q0.x0; q1.ad2 = q1.y0 - q0.y0;
+    }
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>& g, const Diff<T>&, T* e) {
+        const T dxa = g.dx + T(q.ad1), dya = g.dy + T(q.ad2);
+        const T ua = f_fma(T(q.o_c), dxa, dya * T(q.o_s));
+        const T va = f_fma(T(q.o_c), dya, dxa * T(-q.o_s));
+        e[0] = v_ex2(f_fma(ua * ua, T(q.o_hax), (va * va) * T(q.o_hay)));
+    }
     DPH_HD static void set_consts(Par&, const float*) {}
     DPH_HD static void prepare(const float* p, Par& q) {
         q.amp = p[0]; q.x0 = p[1]; q.y0 = p[2]; q.sx = p[3]; q.sy = p[4]; q.th = p[5]; q.off = p[6];

@@ -58,7 +58,7 @@ int model_consts(int model, const float* consts) {
 int auto_group(int M, int model, long long n_fits, bool tail_hidden) {
     // measured on B200 (profiles/): 7x7 -> 2 lanes; 11x11 -> 4, and 2 for the sampled Gaussian from 3e5 fits per call on (5 %
     // faster there: the per-trip scalar work is shared by 16 fits; equal at 1e5, where the longer per-fit latency shows in the
-    // tails); 15x15 -> 4 for the sampled Gaussian, which keeps no per-pixel state in shared memory, 8 otherwise
+    // tails); 15x15 -> 4 for the sampled and the elliptical Gaussian, which keep no per-pixel state in shared memory, 8 otherwise
     if (model == DPHLM_MULTI_EXP_IRF) return M <= 512 ? 16 : 32;  // built for wide groups only (lm_inst_mexp_irf.cu)
     // multi-exponentials keep no per-bin state in shared memory: the narrowest group whose two staging buffers still leave room
     // for three CTAs per SM (measured on 256 bins, bi-exponential + offset: 5.65e7 fits/s at 4 lanes, 5.18e7 at 8, 4.27e7 at
@@ -67,7 +67,7 @@ int auto_group(int M, int model, long long n_fits, bool tail_hidden) {
     if (M <= 64) return 2;
     // (pipelined calls hide the tail under the next call: 2 lanes win from 1e5 fits on, 1.12e8 against 1.04e8 fits/s)
     if (M <= 128) return model == DPHLM_GAUSS2D && (n_fits >= 300000 || (tail_hidden && n_fits >= 50000)) ? 2 : 4;
-    if (M <= 240) return model == DPHLM_GAUSS2D ? 4 : 8;
+    if (M <= 240) return (model == DPHLM_GAUSS2D || model == DPHLM_GAUSS2D_ELLIPTICAL) ? 4 : 8;  // (elliptical, 15x15: 3.24e7 fits/s at 4 lanes, 2.57e7 at 8)
     return 16;
 }
 
