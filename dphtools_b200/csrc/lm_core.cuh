@@ -395,13 +395,16 @@ struct Gauss2D {  // amp, x0, y0, sigma, offset
 struct Gauss2DFixed {
     static constexpr int P = 4, NE = 1, kMinCtas = 3, kUnroll = kPairUnroll;
     struct Par { float amp, x0, y0, off, sig = 1.0f, s2 = 1.0f, nh = -0.5f * 1.4426950408889634f, as2; };
-    struct Step { float d0, d1, d2, d3, nh1, ndd, c2, k0; };
+    struct Step { float d0, d1, d2, d3, nh1, ndd, c2, k0, ad1, ad2; };  // ad1, ad2: the REALISED centre step (fill_tables)
     template <class T> struct Geo { T dx, dy, r2; };
-    template <class T> struct Diff { T dot, dr2; };
+    template <class T> struct Diff { T dot, dr2, r20; };
     static constexpr int kTable = 0;
-    static constexpr bool kStoreE = true;
+    static constexpr bool kStoreE = false;  // the accepted point's exponential is recomputed, see Gauss2D::expo_old
     DPH_HD static int table_floats(int, int) { return 0; }
-    template <class L> DPH_HD static void fill_tables(const L&, const Par&, Par&, Step&, float*, int, int, int) {}
+    template <class L> DPH_HD static void fill_tables(const L&, const Par& q0, Par& q1, Step& st, float*, int, int, int) {
+        st.ad1 = q1.x0 - q0.x0; st.ad2 = q1.y0 - q0.y0;
+    }
+    template <class T> DPH_HD static void expo_old(const Par& q, const Geo<T>&, const Diff<T>& df, T* e) { e[0] = v_ex2(df.r20 * T(q.nh)); }
     DPH_HD static void set_consts(Par& q, const float* consts) {
         if (!consts) return;
         q.sig = consts[0];
@@ -447,6 +450,8 @@ struct Gauss2DFixed {
     template <class T> DPH_HD static void diff(const Par&, const Step& s, const Geo<T>& g1, Diff<T>& df) {
         df.dot = f_fma(g1.dx, T(s.d1), g1.dy * T(s.d2));
         df.dr2 = f_fma(T(-2.0f), df.dot, T(s.ndd));  // r2_new - r2_old
+        const T dxa = g1.dx + T(s.ad1), dya = g1.dy + T(s.ad2);
+        df.r20 = f_fma(dxa, dxa, dya * dya);         // r2_old, from the realised step (the width is a constant: same exponent scale)
     }
     template <class T> DPH_HD static T delta(const Par& a, const Step& s, const Diff<T>& df, const T* ea, const T* eb) {
         T darg = df.dr2 * T(s.nh1);

@@ -66,8 +66,8 @@ int auto_group(int M, int model, long long n_fits, bool tail_hidden) {
     if (model == DPHLM_MULTI_EXP) return M <= 64 ? 2 : M <= 276 ? 4 : M <= 576 ? 8 : M <= 1176 ? 16 : 32;
     if (M <= 64) return 2;
     // (pipelined calls hide the tail under the next call: 2 lanes win from 1e5 fits on, 1.12e8 against 1.04e8 fits/s)
-    if (M <= 128) return model == DPHLM_GAUSS2D && (n_fits >= 300000 || (tail_hidden && n_fits >= 50000)) ? 2 : 4;
-    if (M <= 240) return (model == DPHLM_GAUSS2D || model == DPHLM_GAUSS2D_ELLIPTICAL) ? 4 : 8;  // (elliptical, 15x15: 3.24e7 fits/s at 4 lanes, 2.57e7 at 8)
+    if (M <= 128) return (model == DPHLM_GAUSS2D || model == DPHLM_GAUSS2D_FIXED) && (n_fits >= 300000 || (tail_hidden && n_fits >= 50000)) ? 2 : 4;
+    if (M <= 240) return (model == DPHLM_GAUSS2D || model == DPHLM_GAUSS2D_ELLIPTICAL || model == DPHLM_GAUSS2D_FIXED) ? 4 : 8;  // (elliptical, 15x15: 3.24e7 fits/s at 4 lanes, 2.57e7 at 8)
     return 16;
 }
 
