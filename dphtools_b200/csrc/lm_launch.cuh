@@ -76,7 +76,7 @@ struct KArgs {
     int* error_flag;        // raised if a poller gave up waiting (never in correct operation)
     int budget;             // trips before parking; <= 0: never
     int max_backlog;        // parked fits waiting for a poller beyond which the main kernels stop parking
-    int on_demand_tail;     // != 0: the last wave of fits is claimed on demand, not ahead (IoDevice::stage)
+    int on_demand_tail;     // != 0: the last on_demand_tail / 4 waves of fits are claimed on demand, not ahead (IoDevice::stage)
     int skip_prefit;        // host-side only: DPHLM_FLAG_SKIP_PREFIT
     int no_vec16;           // tuning aid (DPHLM_NO_VEC16): stage with 4-byte copies even where 16-byte ones are possible
     long long n_fits;
@@ -189,11 +189,11 @@ struct IoDevice {
         constexpr int P = Mo::P;
         const int src = __ffs(ln.gmask) - 1;
         const long long groups = (long long)gridDim.x * kWarps * (32 / G);
-        if (a.on_demand_tail && after >= 0 && after + 3 * groups >= a.n_fits) {
+        if (a.on_demand_tail && after >= 0 && after + (3 + a.on_demand_tail / 4) * groups >= a.n_fits) {
             unsigned long long c = 0;
             if (ln.lane == 0) c = *reinterpret_cast<volatile unsigned long long*>(a.counter);
             c = __shfl_sync(ln.gmask, c, src);
-            if ((long long)c + groups >= a.n_fits) { next = -1; return; }
+            if ((long long)c + groups * a.on_demand_tail / 4 >= a.n_fits) { next = -1; return; }
         }
         unsigned long long idx = 0;
         if (ln.lane == 0) idx = atomicAdd(a.counter, 1ull);
@@ -756,7 +756,8 @@ int launch(const KArgs& a0, const ParkLists& pl, DeviceCtx* ctx, cudaStream_t st
     const ParkQueue none{nullptr, nullptr, nullptr, nullptr, 0};
     KArgs a = a0;
     a.counter = counters;
-    a.on_demand_tail = getenv("DPHLM_NO_ON_DEMAND_TAIL") ? 0 : 1;  // tuning aid
+    a.on_demand_tail = getenv("DPHLM_NO_ON_DEMAND_TAIL") ? 0 : 4;  // in quarters of a wave (one wave = one fit per group)
+    if (const char* e = getenv("DPHLM_TAIL_QUARTERS")) { if (a.on_demand_tail && atoi(e) > 0) a.on_demand_tail = atoi(e); }  // tuning aid
     a.no_vec16 = getenv("DPHLM_NO_VEC16") ? 1 : 0;                  // tuning aid
     a.produce = a.consume[0] = a.consume[1] = none;
     a.wait_done[0] = a.wait_done[1] = nullptr;
