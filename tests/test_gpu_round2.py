@@ -248,3 +248,20 @@ def test_128_bit_staging_changes_nothing(monkeypatch):
         r = dph.curve_fit_batch(model, shifted, p0, "mle", w["xaxis"], group_lanes=lanes)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(r.popt.cpu().numpy(), outs[0][0])
+
+
+def test_device_generator_follows_the_host_recipe():
+    """synth.gauss2d_rois_device (the 1e7-ROI generator of bench.py's configs[2] block): seeded, Poisson counts, and the same p0
+    recipe as the host generator -- the batch it makes converges like the host-generated one."""
+    from dphtools_b200 import synth
+
+    dev = torch.device("cuda", 0)
+    a, pa = synth.gauss2d_rois_device(5000, 7, 11, dev, jitter=0.75, chunk=2048)
+    b, pb = synth.gauss2d_rois_device(5000, 7, 11, dev, jitter=0.75, chunk=2048)
+    assert a.shape == (5000, 7, 7) and pa.shape == (5000, 5) and a.dtype == torch.float32
+    assert torch.equal(a, b) and torch.equal(pa, pb)
+    assert torch.equal(a, a.round()) and float(a.min()) >= 0.0
+    np.testing.assert_array_equal(pa.cpu().numpy(), synth.gauss2d_p0(a.cpu().numpy()))
+    r = dph.curve_fit_batch(models.gauss2d, a, pa, "mle")
+    torch.cuda.synchronize()
+    assert float(((r.info >= 1) & (r.info <= 4)).double().mean()) > 0.999
