@@ -120,7 +120,7 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 }
 
 constexpr int kStageExtra = 8;  // floats after the staged ROI: start parameters (<= 7) and one int
-__device__ __forceinline__ bool getenv_no_vec16(const KArgs& a) { return a.no_vec16 != 0; }
+__device__ __forceinline__ bool staging_4byte_only(const KArgs& a) { return a.no_vec16 != 0; }
 
 template <class Stage, class Mo, int G, bool MAIN, bool MLE, bool RESUME>
 struct IoDevice {
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_ctas<Mo>()) dphlm_stage_kerne
     IO io{a, base + stride + kStageExtra};
     // ROIs whose size is a multiple of 16 bytes (8x8, 12x12, 256-bin histograms ...) are staged with 128-bit copies; an 11x11
     // ROI (484 B) is only 4-byte aligned in the batch ("Staging")
-    io.vec16 = !getenv_no_vec16(a) && (M % 4 == 0) && ((reinterpret_cast<size_t>(a.data) & 15) == 0) &&
+    io.vec16 = !staging_4byte_only(a) && (M % 4 == 0) && ((reinterpret_cast<size_t>(a.data) & 15) == 0) &&
                (((__cvta_generic_to_shared(base) | __cvta_generic_to_shared(base + stride + kStageExtra)) & 15) == 0);
     run_stage<Stage, Mo, G>(ln, px, a.opt, io);
     if (a.exit_counter) {  // tell the pollers fed by this kernel when its last CTA has gone
