@@ -519,7 +519,7 @@ def main():
         if not args.no_cpu and world == 1:
             cores = os.cpu_count()
             kind = cpu_kind()
-            n_cpu = max(256, (250 if kind == "reference" else 40) * cores)
+            n_cpu = max(256, (500 if kind == "reference" else 80) * cores)  # ~10-15 core-seconds of the reference
             rate, popt_ref, info_ref, nfev_ref = cpu_reference(sets[0]["data"][:n_cpu], sets[0]["p0"][:n_cpu], cores)
             r0 = step(0)
             torch.cuda.synchronize()
