@@ -529,9 +529,14 @@ def main():
                                                 nfev=r0.nfev[:n_cpu].cpu().numpy()), dict(popt=popt_ref, info=info_ref, nfev=nfev_ref))
             what = ("the reference's own dphtools.utils.lm.curve_fit(method='mle') per ROI (oracle/_ref)" if kind == "reference"
                     else "float64 oracle port of curve_fit(method='mle') (oracle/_ref not built)")
+            # the same sample with the borderline xtol decisions re-made in float64 (DPHLM_FLAG_EXACT_TIES): the reference's flags
+            rx = dph.curve_fit_batch(models.gauss2d, d_data[0][:n_cpu], d_p0[0][:n_cpu], "mle", exact_ties=True)
+            torch.cuda.synchronize()
+            rep_x = parity_report("gauss2d", dict(popt=rx.popt.cpu().numpy(), info=rx.info.cpu().numpy(), nfev=rx.nfev.cpu().numpy()),
+                                  dict(popt=popt_ref, info=info_ref, nfev=nfev_ref))
             out["cpu_baseline"] = {"value": rate, "unit": "fits/s", "cores": cores, "kind": kind,
                                    "sample": "first %d ROIs of input set 0, %s, one process per core" % (n_cpu, what),
-                                   "parity_on_sample": rep}
+                                   "parity_on_sample": rep, "parity_on_sample_exact_ties": rep_x}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
